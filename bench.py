@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — polymuls/s of the fused NTT->pointwise->INTT path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--set III|I|p-I|p-III]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic polynomials:
+  workload (N=1 headline) = qTESLA-III, n=1024, q=8404993, batch 65,536 per GPU (BASELINE.json
+  configs[2], the parameter set the reference is hard-wired to and `metric` is quoted on).
+  x, y, z are 256 MiB each (768 MiB per step > 126 MB L2, so every step streams from HBM).
+Multi-GPU: one process per GPU, each rank owns its own contiguous slice of the batch (weak scaling,
+no data-path collective); the only communication is the max-over-ranks of the timing.
+
+Prints ONE JSON line on rank 0.  `value` = device-resident throughput (CUDA events on the launch
+stream); `e2e` = the same metric through the host-pointer C-ABI call qt_polymul_host with pinned
+host buffers (H2D + kernel + D2H inside the timed region, the reference's own timing convention,
+NTT.cu:2123-2164); `roofline` = HBM view of the fused kernel, `roofline_int` = integer-multiply
+view (the binding one); `cpu_baseline` = the reference's CPU path on this box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SETS = {"I": 0, "III": 1, "p-I": 2, "p-III": 3}
+DEFAULT_BATCH = {0: 65536, 1: 65536, 2: 65536, 3: 32768}  # BASELINE.json configs
+METRIC = "polymuls/sec"
+UNIT = "polymul/s"
+
+
+def algorithmic_counts(n, logn):
+    """bytes = 12n (read x, read y, write z once); modular multiplies =
+    1.5 n log2 n + 2n; 3 integer multiplies per modular multiply (Shoup/Montgomery)."""
+    modmul = 3 * (n // 2) * logn + 2 * n
+    return 12 * n, modmul, 3 * modmul
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+def load_int_peak(sm_mhz_max, sms=148):
+    """Integer-multiply peak in lane-ops/s: measured by tools/ubench on this pool (profiles/), else the
+    nominal 64 IMAD/clk/SM at the max SM clock."""
+    path = os.path.join(ROOT, "profiles", "ubench_int_peak.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            return float(d["imad_tera_lane_ops_per_s"]) * 1e12, "measured (tools/ubench, profiles/ubench_int_peak.json)"
+        except Exception:
+            pass
+    return sms * 64 * sm_mhz_max * 1e6, "nominal 148 SM x 64 IMAD/clk x max SM clock"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the GPU is busy."""
+
+    def __init__(self, index):
+        self.samples = []
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: report it, do not fail the bench
+            self.err = str(e)
+
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append((mhz, int(reasons)))
+        except Exception:
+            pass
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"], "samples": 0}
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        seen = set()
+        for _, r in self.samples:
+            for k, bit in names.items():
+                if r & bit:
+                    seen.add(k)
+        mhz = sorted(m for m, _ in self.samples)
+        med = mhz[len(mhz) // 2] if mhz else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(seen), "samples": len(mhz)}
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, built from the unmodified
+    sources) on all host threads; falls back to the oracle port when _ref was not built."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle_lib import Oracle, Reference
+    set_id = SETS[args.set]
+    o = Oracle()
+    p = o.params(set_id)
+    use_ref = Reference.available() and set_id == 1
+    ref = Reference() if use_ref else None
+    threads = ref.max_threads() if use_ref else o.max_threads()
+    run = (lambda x, y: ref.polymul(x, y, 0, threads)) if use_ref else (lambda x, y: o.polymul(set_id, x, y, threads=threads))
+    # calibrate, then size a step so that the whole run lasts ~20 s
+    cal = 64 * threads
+    x = o.splitmix(1, 0, p.q, cal * p.n)
+    y = o.splitmix(2, 0, p.q, cal * p.n)
+    run(x, y)
+    t0 = time.perf_counter()
+    run(x, y)
+    rate = cal / (time.perf_counter() - t0)
+    per_step = int(max(2 * threads, min(65536, rate * 20.0 / (args.steps + args.warmup))))
+    x = o.splitmix(1, 0, p.q, per_step * p.n)
+    y = o.splitmix(2, 0, p.q, per_step * p.n)
+    for _ in range(args.warmup):
+        run(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(x, y)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    kind = "reference" if use_ref else "port"
+    sample = f"{per_step} polymuls per step x {args.steps} steps (bounded sample of the batch-{DEFAULT_BATCH[set_id]} workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(set_id, p, DEFAULT_BATCH[set_id], args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(set_id, p, batch, gpus):
+    names = {0: "qTESLA-I", 1: "qTESLA-III", 2: "qTESLA-p-I", 3: "qTESLA-p-III"}
+    return {
+        "workload": f"{names[set_id]} n={p.n} q={p.q} batch {batch} per GPU, fused NTT->pointwise->INTT negacyclic polymul",
+        "param_set": names[set_id], "n": int(p.n), "q": int(p.q), "batch_per_gpu": batch,
+        "global_batch": batch * gpus, "parallelism": f"batch-sharded x{gpus}, no collective",
+        "l2": "inputs larger than L2 (x,y,z = %d MiB per step)" % (3 * batch * p.n * 4 >> 20),
+    }
+
+
+def cpu_baseline(set_id, o):
+    """Reference CPU path timed on this box's host cores on a bounded sample (rank 0, N=1 only)."""
+    from oracle_lib import Reference
+    p = o.params(set_id)
+    use_ref = Reference.available() and set_id == 1
+    ref = Reference() if use_ref else None
+    threads = ref.max_threads() if use_ref else o.max_threads()
+    run = (lambda x, y, t: ref.polymul(x, y, 0, t)) if use_ref else (lambda x, y, t: o.polymul(set_id, x, y, threads=t))
+    cal = 32 * threads
+    x = o.splitmix(1, 0, p.q, cal * p.n)
+    y = o.splitmix(2, 0, p.q, cal * p.n)
+    run(x, y, threads)
+    t0 = time.perf_counter()
+    run(x, y, threads)
+    rate = cal / (time.perf_counter() - t0)
+    count = int(max(cal, min(65536, rate * 6.0)))  # ~6 s wall on all threads
+    x = o.splitmix(1, 0, p.q, count * p.n)
+    y = o.splitmix(2, 0, p.q, count * p.n)
+    t0 = time.perf_counter()
+    run(x, y, threads)
+    dt = time.perf_counter() - t0
+    one = min(count, 4096)
+    t1 = time.perf_counter()
+    run(x[: one * p.n], y[: one * p.n], 1)
+    dt1 = time.perf_counter() - t1
+    return {
+        "value": count / dt, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+        "sample": f"first {count} polynomials of the same synthetic stream, all host threads, {dt:.1f} s wall",
+        "value_1thread": one / dt1,
+        "what": ("unmodified reference CPU functions Phi-scale + radix2NTTGS + pointwise + radix2INTT + invPhi "
+                 "(NTT.cu:1058-1084,1473-1494,1826-1849) built into oracle/_ref, OpenMP over polynomial pairs")
+        if use_ref else "oracle/qt_oracle.c port of the same functions (reference not built / other parameter set)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--set", default="III", choices=list(SETS))
+    ap.add_argument("--batch", type=int, default=0, help="polynomials per GPU per step (default: BASELINE config)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other parameter sets / CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from qtesla_b200_loader import load
+    qt = load()
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks, peaks_src = load_peaks()
+    stream = torch.cuda.Stream(device=dev)
+
+    def run_config(set_id, batch, steps, warmup, sampler=None):
+        eng = qt.Engine(set_id, local_rank)
+        eng.set_stream(stream.cuda_stream)
+        p = eng.params
+        words = batch * p.n
+        x = torch.empty(words, dtype=torch.int32, device=dev)
+        y = torch.empty(words, dtype=torch.int32, device=dev)
+        z = torch.empty(words, dtype=torch.int32, device=dev)
+        first = rank * words  # every rank owns its own slice of the global synthetic stream
+        with torch.cuda.stream(stream):
+            eng.fill_uniform(x, 1, first)
+            eng.fill_uniform(y, 2, first)
+            for _ in range(warmup):
+                eng.polymul(x, y, z, batch)
+        stream.synchronize()
+        l0 = eng.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                eng.polymul(x, y, z, batch)
+            e1.record(stream)
+        while not e1.query():  # launches are asynchronous: sample clocks while the GPU works
+            if sampler is not None:
+                sampler.sample()
+            time.sleep(0.002)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = eng.launch_count() - l0
+        return eng, (x, y, z), ms, launches
+
+    set_id = SETS[args.set]
+    batch = args.batch or DEFAULT_BATCH[set_id]
+    sampler = ClockSampler(local_rank)
+    eng, (x, y, z), ms, launches = run_config(set_id, batch, args.steps, args.warmup, sampler)
+    p = eng.params
+    ms_per_step = ms / args.steps
+    value = batch * world * args.steps / (ms * 1e-3)
+    bytes_pp, modmul_pp, imad_pp = algorithmic_counts(p.n, p.logn)
+    kernel_ms = ms_per_step  # one fused kernel per step: the step IS the kernel
+    per_gpu_rate = batch / (kernel_ms * 1e-3)
+    hbm_achieved = per_gpu_rate * bytes_pp / 1e9
+    int_peak, int_src = load_int_peak(float(peaks.get("sm_max_mhz", 1965.0)))
+    int_achieved = per_gpu_rate * imad_pp
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_fused.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(args.set)
+        except Exception:
+            traffic = None
+
+    # parity spot check of the timed buffers against the oracle (first/last polynomials of this shard)
+    parity = None
+    if rank == 0:
+        from oracle_lib import Oracle
+        o = Oracle()
+        idx = list(range(0, 8)) + list(range(batch - 8, batch))
+        xs = np.concatenate([x[i * p.n:(i + 1) * p.n].cpu().numpy().view(np.uint32) for i in idx])
+        ys = np.concatenate([y[i * p.n:(i + 1) * p.n].cpu().numpy().view(np.uint32) for i in idx])
+        zs = np.concatenate([z[i * p.n:(i + 1) * p.n].cpu().numpy().view(np.uint32) for i in idx])
+        gen_ok = bool(np.array_equal(xs[: p.n], o.splitmix(1, 0, p.q, p.n)))
+        parity = bool(np.array_equal(zs, o.polymul(set_id, xs, ys))) and gen_ok
+
+    # end-to-end: host buffers through qt_polymul_host (H2D + kernel + D2H inside the timed region)
+    e2e_steps = max(1, min(args.steps, 10))
+    words = batch * p.n
+    hx = torch.empty(words, dtype=torch.int32).pin_memory()
+    hy = torch.empty(words, dtype=torch.int32).pin_memory()
+    hz = torch.empty(words, dtype=torch.int32).pin_memory()
+    hx.copy_(x)
+    hy.copy_(y)
+    xh, yh, zh = (t.numpy().view(np.uint32) for t in (hx, hy, hz))
+    for _ in range(2):
+        eng.polymul_host(xh, yh, zh, batch)
+    barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.polymul_host(xh, yh, zh, batch)  # synchronous: returns when z is complete in host memory
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = batch * world * e2e_steps / e2e_s
+    e2e_ok = bool(np.array_equal(zh[: 4 * p.n], z[: 4 * p.n].cpu().numpy().view(np.uint32)))
+
+    extras = []
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del hx, hy, hz
+        for name, sid in SETS.items():
+            if sid == set_id:
+                continue
+            e2, _, ms2, _ = run_config(sid, DEFAULT_BATCH[sid], max(3, min(args.steps, 50)), 3)
+            st = max(3, min(args.steps, 50))
+            b2, _, i2 = algorithmic_counts(e2.params.n, e2.params.logn)
+            r2 = DEFAULT_BATCH[sid] * st / (ms2 * 1e-3)
+            extras.append({"param_set": name, "n": int(e2.params.n), "batch": DEFAULT_BATCH[sid], "value": r2, "unit": UNIT,
+                           "hbm_frac": r2 * b2 / 1e9 / float(peaks["hbm_gbs"]), "int_frac": r2 * i2 / int_peak})
+            e2.close()
+        from oracle_lib import Oracle
+        cpu = cpu_baseline(set_id, Oracle())
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic (splitmix64 counter hash, uniform in [0,q), generated on device)",
+            "config": workload_config(set_id, p, batch, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * words * 4, "d2h_bytes_per_step": words * 4,
+                    "steps": e2e_steps, "api": "qt_polymul_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)",
+                    "matches_device_result": e2e_ok},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                         "frac": hbm_achieved / float(peaks["hbm_gbs"]), "traffic": traffic,
+                         "peak_source": peaks_src, "kernel": "k_polymul", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": bytes_pp * batch,
+                         "note": "HBM view; the binding roofline is the integer-multiply pipe, see roofline_int"},
+            "roofline_int": {"bound": "int_mul", "achieved": int_achieved / 1e12, "peak": int_peak / 1e12,
+                             "unit": "T int32-mul/s", "frac": int_achieved / int_peak, "peak_source": int_src,
+                             "algorithmic_mul_per_polymul": imad_pp},
+            "parity_spot_check": parity,
+            "kernel_info": eng.kernel_info(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if extras:
+            line["other_configs"] = extras
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,443 @@
+// qt_capi.cu — the extern "C" boundary (include/qtesla_b200.h) and the host-side runtime:
+// contexts (device tables + stream), launch geometry, chunked H2D/compute/D2H pipeline for the
+// harness-equivalent host-pointer entry points, and contiguous batch sharding over GPUs.
+//
+// There is NO CPU fallback here: every compute entry point launches a CUDA kernel or returns an
+// error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/qtesla_b200.h"
+#include "qt_kernels.cuh"
+#include "qt_nussbaumer.cuh"
+
+namespace qt {
+TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX];
+}
+
+using namespace qt;
+
+#define QT_CUDA(call)                                \
+    do {                                             \
+        cudaError_t e__ = (call);                    \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+
+struct qt_ctx {
+    int set = -1;
+    int device = -1;
+    RtParams p{};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    TwQuad* d_lane_fwd = nullptr;
+    TwQuad* d_lane_inv = nullptr;
+    int num_sms = 0;
+    int grid_fused = 0, grid_fwd = 0, grid_inv = 0, grid_nuss = 0;
+    int occ_fused = 0;
+    size_t smem_fused = 0, smem_one = 0;
+    uint64_t launches = 0;
+    // host pipeline (qt_polymul_host): lazily created
+    static constexpr int PIPE = 3;
+    cudaStream_t pipe_stream[PIPE] = {nullptr, nullptr, nullptr};
+    uint32_t* pipe_buf[PIPE] = {nullptr, nullptr, nullptr};  // x | y per slot, z overwrites x
+    size_t pipe_polys = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+std::mutex g_uni_mutex;
+bool g_uni_uploaded[64][NUM_SETS];  // per device
+
+template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
+    using S = KernelShape<SET>;
+    c->smem_fused = S::SMEM_FUSED;
+    c->smem_one = S::SMEM_ONE;
+    QT_CUDA(cudaFuncSetAttribute(k_polymul<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_FUSED));
+    QT_CUDA(cudaFuncSetAttribute(k_ntt_forward<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_ONE));
+    QT_CUDA(cudaFuncSetAttribute(k_ntt_inverse<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_ONE));
+    int occ = 0;
+    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polymul<SET>, WARPS_PER_CTA * 32, S::SMEM_FUSED));
+    if (occ < 1) return QT_ERR_UNSUPPORTED;
+    c->occ_fused = occ;
+    c->grid_fused = occ * c->num_sms;
+    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_forward<SET>, WARPS_PER_CTA * 32, S::SMEM_ONE));
+    c->grid_fwd = std::max(1, occ) * c->num_sms;
+    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_inverse<SET>, WARPS_PER_CTA * 32, S::SMEM_ONE));
+    c->grid_inv = std::max(1, occ) * c->num_sms;
+    int rc = nuss_setup<SET>(c->num_sms, &c->grid_nuss);
+    if (rc) return rc;
+    (void)T;
+    return 0;
+}
+
+int upload_tables(qt_ctx* c) {
+    HostTables T;
+    build_tables(c->set, &T);
+    const size_t quads = T.lane_fwd.size();
+    QT_CUDA(cudaMalloc(&c->d_lane_fwd, quads * sizeof(TwQuad)));
+    QT_CUDA(cudaMalloc(&c->d_lane_inv, quads * sizeof(TwQuad)));
+    QT_CUDA(cudaMemcpy(c->d_lane_fwd, T.lane_fwd.data(), quads * sizeof(TwQuad), cudaMemcpyHostToDevice));
+    QT_CUDA(cudaMemcpy(c->d_lane_inv, T.lane_inv.data(), quads * sizeof(TwQuad), cudaMemcpyHostToDevice));
+    {
+        std::lock_guard<std::mutex> lk(g_uni_mutex);
+        memcpy(h_uni[c->set], T.uni, sizeof(T.uni));
+        if (c->device < 64 && !g_uni_uploaded[c->device][c->set]) {
+            QT_CUDA(cudaMemcpyToSymbol(c_uni, T.uni, sizeof(T.uni), (size_t)c->set * sizeof(T.uni)));
+            g_uni_uploaded[c->device][c->set] = true;
+        } else if (c->device >= 64) {
+            QT_CUDA(cudaMemcpyToSymbol(c_uni, T.uni, sizeof(T.uni), (size_t)c->set * sizeof(T.uni)));
+        }
+    }
+    switch (c->set) {
+    case SET_I: return setup_set<SET_I>(c, T);
+    case SET_III: return setup_set<SET_III>(c, T);
+    case SET_P_I: return setup_set<SET_P_I>(c, T);
+    default: return setup_set<SET_P_III>(c, T);
+    }
+}
+
+inline int grid_for(int max_grid, size_t tiles) {
+    size_t ctas = (tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)max_grid, ctas));
+}
+
+template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B,
+                                      cudaStream_t s) {
+    const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
+    k_polymul<SET><<<grid_for(c->grid_fused, tiles), WARPS_PER_CTA * 32, c->smem_fused, s>>>(
+        x, y, z, B, c->d_lane_fwd, c->d_lane_inv);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
+    const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
+    k_ntt_forward<SET><<<grid_for(c->grid_fwd, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_fwd);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+template <int SET> int launch_inverse(qt_ctx* c, uint32_t* a, size_t B) {
+    const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
+    k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_inv);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+template <int SET> int launch_pointwise(qt_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t B) {
+    const size_t words = B * Cfg<SET>::N;
+    const int grid = (int)std::min<size_t>((size_t)c->num_sms * 8, (words / 4 + 255) / 256);
+    k_pointwise<SET><<<std::max(1, grid), 256, 0, c->stream>>>(a, b, o, words);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+template <int SET> int launch_bitrev(qt_ctx* c, const uint32_t* in, uint32_t* out, size_t B) {
+    const size_t words = B * Cfg<SET>::N;
+    const int grid = (int)std::min<size_t>((size_t)c->num_sms * 8, (words + 255) / 256);
+    k_bitrev_copy<SET><<<std::max(1, grid), 256, 0, c->stream>>>(in, out, words);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
+#define QT_DISPATCH(c, fn, ...)                                  \
+    ((c)->set == SET_I       ? fn<SET_I>(__VA_ARGS__)            \
+     : (c)->set == SET_III   ? fn<SET_III>(__VA_ARGS__)          \
+     : (c)->set == SET_P_I   ? fn<SET_P_I>(__VA_ARGS__)          \
+                             : fn<SET_P_III>(__VA_ARGS__))
+
+int ensure_pipe(qt_ctx* c) {
+    if (c->pipe_buf[0]) return 0;
+    // chunk: 4096 polynomials of n=1024 (16 MiB per operand) — large enough for PCIe efficiency,
+    // small enough that three slots overlap H2D, compute and D2H
+    c->pipe_polys = (size_t)(4u << 20) / c->p.n;
+    for (int i = 0; i < qt_ctx::PIPE; i++) {
+        QT_CUDA(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));
+        QT_CUDA(cudaMalloc(&c->pipe_buf[i], 2 * c->pipe_polys * c->p.n * sizeof(uint32_t)));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qt_version(void) { return "qtesla_b200 0.1 (sm_100a)"; }
+
+const char* qt_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    switch (code) {
+    case QT_ERR_BAD_SET: return "unknown parameter set";
+    case QT_ERR_BAD_ARG: return "bad argument";
+    case QT_ERR_NO_DEVICE: return "no usable CUDA device";
+    case QT_ERR_UNSUPPORTED: return "unsupported on this device/parameter set";
+    case QT_ERR_NOMEM: return "out of memory";
+    default: return "unknown error";
+    }
+}
+
+int qt_get_params(int set, qt_params* out) {
+    RtParams p;
+    if (!out) return QT_ERR_BAD_ARG;
+    if (!rt_params(set, &p)) return QT_ERR_BAD_SET;
+    out->set = set; out->n = p.n; out->logn = p.logn; out->q = p.q;
+    out->psi = p.psi; out->psi_inv = p.psi_inv; out->omega = p.omega; out->omega_inv = p.omega_inv;
+    out->n_inv = p.n_inv; out->qinv_neg = p.qinv_neg;
+    out->barrett_mu48 = (uint32_t)((1ull << 48) / p.q);
+    return 0;
+}
+
+int qt_get_table(int set, int which, uint32_t* out) {
+    RtParams p;
+    if (!out) return QT_ERR_BAD_ARG;
+    if (!rt_params(set, &p)) return QT_ERR_BAD_SET;
+    HostTables T;
+    build_tables(set, &T);
+    const std::vector<uint32_t>* src = which == QT_TABLE_BITREV ? &T.bitrev : which == QT_TABLE_PHI ? &T.Phi
+                                     : which == QT_TABLE_INVPHI ? &T.invPhi : which == QT_TABLE_TF0 ? &T.tf0
+                                     : which == QT_TABLE_TI0 ? &T.ti0 : nullptr;
+    if (!src) return QT_ERR_BAD_ARG;
+    memcpy(out, src->data(), p.n * sizeof(uint32_t));
+    return 0;
+}
+
+int qt_device_count(int* out) {
+    if (!out) return QT_ERR_BAD_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return (int)e; }
+    *out = n;
+    return 0;
+}
+
+int qt_create(int set, int device, qt_ctx** out) {
+    RtParams p;
+    if (!out) return QT_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!rt_params(set, &p)) return QT_ERR_BAD_SET;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return QT_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return QT_ERR_BAD_ARG;
+    DeviceGuard g(device);
+    if (!g.ok) return QT_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    QT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return QT_ERR_UNSUPPORTED;  // sm_100a cubin only
+    qt_ctx* c = new (std::nothrow) qt_ctx();
+    if (!c) return QT_ERR_NOMEM;
+    c->set = set; c->device = device; c->p = p; c->num_sms = prop.multiProcessorCount;
+    int rc = (int)cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (!rc) { c->stream = c->own_stream; rc = upload_tables(c); }
+    if (rc) { qt_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+int qt_destroy(qt_ctx* c) {
+    if (!c) return 0;
+    DeviceGuard g(c->device);
+    for (int i = 0; i < qt_ctx::PIPE; i++) {
+        if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
+        if (c->pipe_stream[i]) cudaStreamDestroy(c->pipe_stream[i]);
+    }
+    if (c->d_lane_fwd) cudaFree(c->d_lane_fwd);
+    if (c->d_lane_inv) cudaFree(c->d_lane_inv);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int qt_set_stream(qt_ctx* c, void* s) {
+    if (!c) return QT_ERR_BAD_ARG;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int qt_synchronize(qt_ctx* c) {
+    if (!c) return QT_ERR_BAD_ARG;
+    DeviceGuard g(c->device);
+    QT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int qt_device_malloc(qt_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return QT_ERR_BAD_ARG;
+    DeviceGuard g(c->device);
+    QT_CUDA(cudaMalloc(out, bytes));
+    return 0;
+}
+int qt_device_free(qt_ctx* c, void* d) {
+    if (!c) return QT_ERR_BAD_ARG;
+    DeviceGuard g(c->device);
+    QT_CUDA(cudaFree(d));
+    return 0;
+}
+int qt_host_alloc(size_t bytes, void** out) {
+    if (!out) return QT_ERR_BAD_ARG;
+    QT_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return 0;
+}
+int qt_host_free(void* h) {
+    QT_CUDA(cudaFreeHost(h));
+    return 0;
+}
+int qt_memcpy_h2d(qt_ctx* c, void* d, const void* h, size_t bytes) {
+    if (!c) return QT_ERR_BAD_ARG;
+    DeviceGuard g(c->device);
+    QT_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+int qt_memcpy_d2h(qt_ctx* c, void* h, const void* d, size_t bytes) {
+    if (!c) return QT_ERR_BAD_ARG;
+    DeviceGuard g(c->device);
+    QT_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+int qt_ntt_forward(qt_ctx* c, uint32_t* a, size_t B) {
+    if (!c || (!a && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_forward, c, a, B);
+}
+int qt_ntt_inverse(qt_ctx* c, uint32_t* a, size_t B) {
+    if (!c || (!a && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_inverse, c, a, B);
+}
+int qt_pointwise(qt_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t B) {
+    if (!c || ((!a || !b || !o) && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_pointwise, c, a, b, o, B);
+}
+int qt_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B) {
+    if (!c || ((!x || !y || !z) && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_polymul, c, x, y, z, B, c->stream);
+}
+int qt_bitrev_copy(qt_ctx* c, const uint32_t* in, uint32_t* out, size_t B) {
+    if (!c || ((!in || !out) && B) || (in == out && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_bitrev, c, in, out, B);
+}
+int qt_nussbaumer(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ring) {
+    if (!c || ((!x || !y || !z) && B) || (ring != QT_RING_2P32M1 && ring != QT_RING_MODQ)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    int rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, x, y, z, B, ring, c->stream);
+    if (rc == 0) c->launches++;
+    return rc;
+}
+int qt_fill_uniform(qt_ctx* c, uint32_t* a, size_t count, uint64_t seed, uint64_t first) {
+    if (!c || (!a && count)) return QT_ERR_BAD_ARG;
+    if (!count) return 0;
+    DeviceGuard g(c->device);
+    const int grid = (int)std::min<size_t>((size_t)c->num_sms * 8, (count + 255) / 256);
+    k_fill_uniform<<<std::max(1, grid), 256, 0, c->stream>>>(a, count, seed, first, c->p.q);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
+// Host-pointer product: chunks of pipe_polys polynomials rotate through PIPE device slots; each
+// slot's stream does H2D(x,y) -> kernel -> D2H(z), so copies of neighbouring chunks overlap with
+// compute and with each other (PCIe is full duplex).
+static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int nuss_ring) {
+    if (!c || ((!x || !y || !z) && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    int rc = ensure_pipe(c);
+    if (rc) return rc;
+    const size_t n = c->p.n, chunk = c->pipe_polys;
+    size_t done = 0;
+    int slot = 0;
+    while (done < B) {
+        const size_t cnt = std::min(chunk, B - done);
+        const size_t bytes = cnt * n * sizeof(uint32_t);
+        cudaStream_t s = c->pipe_stream[slot];
+        uint32_t* dx = c->pipe_buf[slot];
+        uint32_t* dy = dx + chunk * n;
+        QT_CUDA(cudaMemcpyAsync(dx, x + done * n, bytes, cudaMemcpyHostToDevice, s));
+        QT_CUDA(cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s));
+        if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
+        else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, s); if (!rc) c->launches++; }
+        if (rc) return rc;
+        QT_CUDA(cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s));
+        done += cnt;
+        slot = (slot + 1) % qt_ctx::PIPE;
+    }
+    for (int i = 0; i < qt_ctx::PIPE; i++) QT_CUDA(cudaStreamSynchronize(c->pipe_stream[i]));
+    return 0;
+}
+
+int qt_polymul_host(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B) {
+    return host_pipeline(c, x, y, z, B, -1);
+}
+int qt_nussbaumer_host(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ring) {
+    if (ring != QT_RING_2P32M1 && ring != QT_RING_MODQ) return QT_ERR_BAD_ARG;
+    return host_pipeline(c, x, y, z, B, ring);
+}
+
+int qt_polymul_host_multi(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ngpus) {
+    RtParams p;
+    if (!rt_params(set, &p)) return QT_ERR_BAD_SET;
+    if ((!x || !y || !z) && B) return QT_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return QT_ERR_NO_DEVICE;
+    if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
+    if (!B) return 0;
+    // contiguous slices [g*B/G, (g+1)*B/G), one host thread per device, no collective
+    std::vector<int> rcs(ngpus, 0);
+    std::vector<std::thread> th;
+    for (int gidx = 0; gidx < ngpus; gidx++) {
+        th.emplace_back([&, gidx]() {
+            const size_t lo = B * gidx / ngpus, hi = B * (gidx + 1) / ngpus;
+            if (hi == lo) return;
+            qt_ctx* c = nullptr;
+            int rc = qt_create(set, gidx, &c);
+            if (!rc) rc = qt_polymul_host(c, x + lo * p.n, y + lo * p.n, z + lo * p.n, hi - lo);
+            qt_destroy(c);
+            rcs[gidx] = rc;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int rc : rcs)
+        if (rc) return rc;
+    return 0;
+}
+
+int qt_launch_count(qt_ctx* c, uint64_t* out) {
+    if (!c || !out) return QT_ERR_BAD_ARG;
+    *out = c->launches;
+    return 0;
+}
+
+int qt_kernel_info(qt_ctx* c, int* grid, int* block, int* smem, int* per_sm, int* sms) {
+    if (!c) return QT_ERR_BAD_ARG;
+    if (grid) *grid = c->grid_fused;
+    if (block) *block = WARPS_PER_CTA * 32;
+    if (smem) *smem = (int)c->smem_fused;
+    if (per_sm) *per_sm = c->occ_fused;
+    if (sms) *sms = c->num_sms;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+// qt_emu.cpp — TEST INFRASTRUCTURE: lane-by-lane CPU execution of the warp-tile engine.
+//
+// Compiles ntt-gpu-qtesla_b200/csrc/qt_tile.cuh for the host and runs the same phase sequence as
+// the CUDA kernels of qt_kernels.cuh, with the 32 lanes of a warp executed one after another between
+// the kernels' __syncwarp points.  This checks the index arithmetic, the lazy-reduction bounds
+// (true 32-bit wrap-around) and the twiddle tables without a GPU.  It is never loaded by the product.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../ntt-gpu-qtesla_b200/csrc/qt_tile.cuh"
+
+namespace qt {
+TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX];
+}
+using namespace qt;
+
+namespace {
+
+template <int SET> struct Emu {
+    using T = Tile<SET>;
+    static constexpr uint32_t E = T::E;
+    HostTables tab;
+    Emu() {
+        build_tables(SET, &tab);
+        memcpy(h_uni[SET], tab.uni, sizeof(tab.uni));
+    }
+    const TwQuad* twf(uint32_t lane) const { return tab.lane_fwd.data() + lane % T::BLOCKS; }
+    const TwQuad* twi(uint32_t lane) const { return tab.lane_inv.data() + lane % T::BLOCKS; }
+
+    void polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+        alignas(16) static uint32_t buf[64 * 32];
+        const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+        std::vector<uint32_t> VX(32 * E), VY(32 * E);
+        auto vx = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&VX[lane * E]); };
+        auto vy = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&VY[lane * E]); };
+        for (size_t tile = 0; tile < ntiles; tile++) {
+            const size_t base = tile * T::C::TILE_WORDS;
+            auto valid = [&](uint32_t lane) { return tile * T::PPW + lane / T::LPP < batch; };
+            for (uint32_t l = 0; l < 32; l++) {
+                T::load_rows(vx(l), x + base, l, valid(l));
+                T::load_rows(vy(l), y + base, l, valid(l));
+                T::fwd_rows(vx(l));
+                T::sts_rows(vx(l), buf, l);
+            }
+            for (uint32_t l = 0; l < 32; l++) T::lds_cols(vx(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) {
+                T::fwd_rows(vy(l));
+                T::sts_rows(vy(l), buf, l);
+                T::fwd_cols(vx(l), twf(l));
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                T::lds_cols(vy(l), buf, l);
+                T::fwd_cols(vy(l), twf(l));
+                T::pointwise_mont(vy(l), vx(l));
+                T::inv_cols(vy(l), twi(l));
+            }
+            for (uint32_t l = 0; l < 32; l++) T::sts_cols(vy(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) T::lds_rows(vy(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) {
+                T::template inv_rows<UNI_INV_FUSED>(vy(l));
+                T::store_rows(vy(l), z + base, l, valid(l));
+            }
+        }
+    }
+
+    void forward(uint32_t* a, size_t batch) {
+        alignas(16) static uint32_t buf[64 * 32];
+        const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+        std::vector<uint32_t> V(32 * E);
+        auto v = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&V[lane * E]); };
+        for (size_t tile = 0; tile < ntiles; tile++) {
+            const size_t base = tile * T::C::TILE_WORDS;
+            auto valid = [&](uint32_t lane) { return tile * T::PPW + lane / T::LPP < batch; };
+            for (uint32_t l = 0; l < 32; l++) {
+                T::load_rows(v(l), a + base, l, valid(l));
+                T::fwd_rows(v(l));
+                T::sts_rows(v(l), buf, l);
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                T::lds_cols(v(l), buf, l);
+                T::fwd_cols(v(l), twf(l));
+                T::canon_fwd(v(l));
+            }
+            for (uint32_t l = 0; l < 32; l++) T::sts_cols(v(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) T::lds_rows(v(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) T::store_rows(v(l), a + base, l, valid(l));
+        }
+    }
+
+    void inverse(uint32_t* a, size_t batch) {
+        alignas(16) static uint32_t buf[64 * 32];
+        const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+        std::vector<uint32_t> V(32 * E);
+        auto v = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&V[lane * E]); };
+        for (size_t tile = 0; tile < ntiles; tile++) {
+            const size_t base = tile * T::C::TILE_WORDS;
+            auto valid = [&](uint32_t lane) { return tile * T::PPW + lane / T::LPP < batch; };
+            for (uint32_t l = 0; l < 32; l++) {
+                T::load_rows(v(l), a + base, l, valid(l));
+                T::sts_rows(v(l), buf, l);
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                T::lds_cols(v(l), buf, l);
+                T::inv_cols(v(l), twi(l));
+            }
+            for (uint32_t l = 0; l < 32; l++) T::sts_cols(v(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) T::lds_rows(v(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) {
+                T::template inv_rows<UNI_INV_PLAIN>(v(l));
+                T::store_rows(v(l), a + base, l, valid(l));
+            }
+        }
+    }
+
+    // worst bank-conflict degree of the four shared-memory access patterns
+    // (32-bit: 32 lanes per wavefront; 128-bit: 8 lanes per wavefront, 4 banks each)
+    int bank_conflicts() {
+        int worst = 1;
+        for (uint32_t r = 0; r < E; r++) {
+            int cnt[32] = {0};
+            for (uint32_t l = 0; l < 32; l++) cnt[T::swz(T::row_off(l, r)) % 32]++;
+            for (int b = 0; b < 32; b++) worst = cnt[b] > worst ? cnt[b] : worst;
+        }
+        for (uint32_t c = 0; c < E / 4; c++)
+            for (uint32_t q8 = 0; q8 < 4; q8++) {
+                int cnt[32] = {0};
+                for (uint32_t l = q8 * 8; l < q8 * 8 + 8; l++) {
+                    const uint32_t p = T::swz(E * l + 4 * c);
+                    if (p % 4) return -1;  // 128-bit access must stay aligned
+                    for (int k = 0; k < 4; k++) cnt[(p + k) % 32]++;
+                }
+                for (int b = 0; b < 32; b++) worst = cnt[b] > worst ? cnt[b] : worst;
+            }
+        // the swizzle must be a permutation of the tile
+        std::vector<uint8_t> seen(T::C::TILE_WORDS, 0);
+        for (uint32_t o = 0; o < T::C::TILE_WORDS; o++) {
+            const uint32_t p = T::swz(o);
+            if (p >= T::C::TILE_WORDS || seen[p]) return -2;
+            seen[p] = 1;
+        }
+        return worst;
+    }
+};
+
+template <int SET> Emu<SET>& emu() {
+    static Emu<SET> e;
+    return e;
+}
+
+}  // namespace
+
+#define EMU_DISPATCH(set, call)                  \
+    switch (set) {                               \
+    case SET_I: emu<SET_I>().call; break;        \
+    case SET_III: emu<SET_III>().call; break;    \
+    case SET_P_I: emu<SET_P_I>().call; break;    \
+    case SET_P_III: emu<SET_P_III>().call; break; \
+    default: return -1;                          \
+    }
+
+extern "C" {
+int qtemu_polymul(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    EMU_DISPATCH(set, polymul(x, y, z, batch));
+    return 0;
+}
+int qtemu_forward(int set, uint32_t* a, size_t batch) {
+    EMU_DISPATCH(set, forward(a, batch));
+    return 0;
+}
+int qtemu_inverse(int set, uint32_t* a, size_t batch) {
+    EMU_DISPATCH(set, inverse(a, batch));
+    return 0;
+}
+int qtemu_bank_conflicts(int set) {
+    int r = 0;
+    switch (set) {
+    case SET_I: r = emu<SET_I>().bank_conflicts(); break;
+    case SET_III: r = emu<SET_III>().bank_conflicts(); break;
+    case SET_P_I: r = emu<SET_P_I>().bank_conflicts(); break;
+    case SET_P_III: r = emu<SET_P_III>().bank_conflicts(); break;
+    default: return -9;
+    }
+    return r;
+}
+}

@@ -1,0 +1,105 @@
+// ubench.cu — integer-pipe micro-benchmark for the roofline denominator (SURVEY.md 8d asks for the
+// IMAD rate to be confirmed on the box).  Measures sustained warp-instruction throughput of the
+// integer multiply forms a Shoup/Montgomery butterfly can be built from, and of the ALU ops beside
+// them, as ops/clk/SM (clock64) and ops/s (CUDA events).  Prints one JSON object.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/ubench tools/ubench.cu
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+constexpr int CHAINS = 8, UNROLL = 16;
+
+template <int OP> __device__ __forceinline__ void step(uint32_t (&r)[CHAINS], uint64_t (&w)[CHAINS], uint32_t b, uint32_t c) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) {
+        if (OP == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));
+        if (OP == 1) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
+        if (OP == 2) {  // multiplicand depends on the accumulator so ptxas cannot hoist the product
+            uint32_t lo = (uint32_t)w[i];
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(lo), "r"(b));
+        }
+        if (OP == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
+        if (OP == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(b), "r"(c));
+        if (OP == 5) asm volatile("min.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
+        if (OP == 6) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));
+        if (OP == 7) {  // Shoup butterfly: 1 mul.hi + 2 mad.lo + 2 add (the fused kernel's inner op)
+            uint32_t hi, t;
+            asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(r[i]), "r"(c));
+            asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(r[i]), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(hi), "r"(0u - 8404993u));
+            uint32_t x = (uint32_t)w[i];
+            asm volatile("add.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(x), "r"(t));
+            asm volatile("sub.u32 %0, %1, %2;" : "=r"(x) : "r"(x), "r"(t));
+            w[i] = x;
+        }
+        if (OP == 8) {  // 1 mad.lo + 1 add interleaved: can both pipes issue every cycle?
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));
+            uint32_t x = (uint32_t)w[i];
+            asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(b));
+            w[i] = x;
+        }
+        if (OP == 9) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(r[i]));
+    }
+}
+
+template <int OP> __global__ void __launch_bounds__(256) k(uint32_t* out, long long* cyc, uint32_t b, uint32_t c, int iters) {
+    uint32_t r[CHAINS];
+    uint64_t w[CHAINS];
+    for (int i = 0; i < CHAINS; i++) { r[i] = threadIdx.x * 7 + i + b; w[i] = r[i] + c; }
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) step<OP>(r, w, b, c);
+    }
+    long long t1 = clock64();
+    uint32_t s = 0;
+    for (int i = 0; i < CHAINS; i++) s += r[i] + (uint32_t)w[i] + (uint32_t)(w[i] >> 32);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP> void run(const char* name, int instr_per_step, int sms, uint32_t* out, long long* cyc, bool last) {
+    const int ctas_per_sm = 4, block = 256, iters = 2000;
+    const int grid = sms * ctas_per_sm;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<OP><<<grid, block>>>(out, cyc, 12345u, 67891u, 10);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    k<OP><<<grid, block>>>(out, cyc, 12345u, 67891u, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> h(grid);
+    cudaMemcpy(h.data(), cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (auto v : h) mx = v > mx ? v : mx;
+    const double thread_instr = (double)iters * UNROLL * CHAINS * instr_per_step;
+    const double total = thread_instr * grid * block;
+    const double per_clk_sm = thread_instr * ctas_per_sm * block / (double)mx;  // lane-ops / clk / SM
+    printf("  \"%s\": {\"lane_ops_per_clk_per_sm\": %.2f, \"tera_lane_ops_per_s\": %.3f, \"ms\": %.3f, \"sm_mhz_effective\": %.0f}%s\n",
+           name, per_clk_sm, total / (ms * 1e-3) / 1e12, ms, mx / (ms * 1e-3) / 1e6, last ? "" : ",");
+}
+
+int main() {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) { printf("{\"error\": \"no device\"}\n"); return 1; }
+    uint32_t* out; long long* cyc;
+    cudaMalloc(&out, (size_t)p.multiProcessorCount * 4 * 256 * sizeof(uint32_t));
+    cudaMalloc(&cyc, (size_t)p.multiProcessorCount * 4 * sizeof(long long));
+    printf("{\n  \"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d,\n", p.name, p.multiProcessorCount, p.clockRate);
+    run<0>("mad_lo_u32", 1, p.multiProcessorCount, out, cyc, false);
+    run<1>("mul_hi_u32", 1, p.multiProcessorCount, out, cyc, false);
+    run<6>("mad_hi_u32", 1, p.multiProcessorCount, out, cyc, false);
+    run<2>("mad_wide_u32", 1, p.multiProcessorCount, out, cyc, false);
+    run<3>("add_u32", 1, p.multiProcessorCount, out, cyc, false);
+    run<4>("lop3", 1, p.multiProcessorCount, out, cyc, false);
+    run<5>("min_u32", 1, p.multiProcessorCount, out, cyc, false);
+    run<9>("shfl_bfly", 1, p.multiProcessorCount, out, cyc, false);
+    run<8>("mad_lo_plus_add (2 instr)", 2, p.multiProcessorCount, out, cyc, false);
+    run<7>("shoup_butterfly (5 instr, 3 mul)", 5, p.multiProcessorCount, out, cyc, true);
+    printf("}\n");
+    return 0;
+}
