@@ -1,8 +1,307 @@
-// qt_nussbaumer.cuh — Nussbaumer negacyclic convolution kernels (placeholder until implemented)
+// qt_nussbaumer.cuh — batched Nussbaumer negacyclic convolution (the NTT-free alternative).
+//
+// The reference has this only as a single-polynomial CPU function (nussbaumer_fft, NTT.cu:167-277,
+// ring macros NTT.cu:102-134); there is no reference GPU kernel.  Structure (n = m*r):
+//   rows X_i[j] = x[m*j+i], rows m..2m-1 are copies         (NTT.cu:185-193)
+//   log2(m) forward stages of rotate-and-add row butterflies  (NTT.cu:195-235)   — no multiplies
+//   2m negacyclic schoolbook products of length r             (NTT.cu:237-239, naive 147-165)
+//   log2(m)+1 inverse stages with halving                     (NTT.cu:241-269)
+//   recombination with u^m = w                                (NTT.cu:271-276)
+// Two rings:
+//   RING 0: Z/(2^32-1) with the reference's end-around-carry macros, every operation in the
+//           reference's order, so even the representation of zero (0 vs 0xFFFFFFFF) is bit-exact;
+//   RING 1: Z_q — same index maps, arithmetic mod q, canonical output; equals the NTT product.
+//
+// Mapping: a CTA of 128 threads works on P = 128/(2m) polynomials at a time, all rows in shared
+// memory (row stride r+1 words: conflict-free both along a row and down a column).
+//   * stage phases: one WARP owns a whole row butterfly (lane = coefficient), reads then writes;
+//   * product phase: one THREAD owns a whole row: x, y in registers, r*r multiply-accumulates with
+//     no communication at all (IMAD.WIDE back to back);
+//   * __syncthreads only between phases.
+// The phase functions are __host__ __device__ so tests/emu can run them thread by thread.
 #pragma once
-#include <cuda_runtime.h>
-#include "qt_params.h"
+#include <cstddef>
+#include <cstdint>
+
+#include "qt_tile.cuh"
+
 namespace qt {
-template <int SET> int nuss_setup(int num_sms, int* grid) { *grid = num_sms; return 0; }
-template <int SET> int nuss_launch(int, const uint32_t*, const uint32_t*, uint32_t*, size_t, int, cudaStream_t) { return -4; }
+
+template <int SET> struct NussCfg {
+    using C = Cfg<SET>;
+    static constexpr uint32_t N = C::N, Q = C::Q;
+    static constexpr uint32_t M = (N == 512) ? 16 : 32;
+    static constexpr uint32_t R = N / M;           // 32, 32, 64
+    static constexpr uint32_t LOGM = c_log2(M);
+    static constexpr uint32_t ROWS = 2 * M;
+    static constexpr uint32_t THREADS = 128;
+    static constexpr uint32_t P = THREADS / ROWS;  // polynomials per CTA pass: 4, 2, 2
+    static constexpr uint32_t XS = R + 1;          // X row stride (words)
+    static constexpr uint32_t YS = (R == 64) ? 2 * R + 1 : R + 1;  // Y rows are doubled in place for r=64
+    static constexpr uint32_t X_WORDS = ROWS * XS, Y_WORDS = ROWS * YS;
+    static constexpr uint32_t POLY_WORDS = X_WORDS + Y_WORDS;
+    static constexpr size_t SMEM_BYTES = (size_t)P * POLY_WORDS * sizeof(uint32_t);
+    static constexpr uint32_t ROT_UNIT = R / M;    // w^(r/m) is the 2m-th root of unity
+};
+
+// ---- ring arithmetic --------------------------------------------------------------------------
+template <int SET, int RING> struct NussOps;
+
+template <int SET> struct NussOps<SET, 0> {  // Z/(2^32-1), NTT.cu:102-134
+    static QT_HD uint32_t add(uint32_t a, uint32_t b) { uint32_t t = a + b; return t + (uint32_t)(t < a); }
+    static QT_HD uint32_t sub(uint32_t a, uint32_t b) { return (a - b) - (uint32_t)(b > a); }
+    static QT_HD uint32_t norm(uint32_t a) { return a + (uint32_t)(a == 0xFFFFFFFFu); }
+    static QT_HD uint32_t neg(uint32_t a) { return norm(0xFFFFFFFFu - a); }
+    static QT_HD uint32_t half(uint32_t a) {
+        a = norm(a);
+        return (uint32_t)(((uint64_t)a + (uint64_t)(uint32_t)(0u - (a & 1u))) >> 1);
+    }
+    static QT_HD uint32_t fold(uint64_t t) { return add((uint32_t)t, (uint32_t)(t >> 32)); }
+};
+
+template <int SET> struct NussOps<SET, 1> {  // Z_q, operands canonical
+    static constexpr uint32_t Q = Cfg<SET>::Q;
+    static QT_HD uint32_t csub(uint32_t a) { return umin32(a, a - Q); }
+    static QT_HD uint32_t add(uint32_t a, uint32_t b) { return csub(a + b); }
+    static QT_HD uint32_t sub(uint32_t a, uint32_t b) { return csub(a - b + Q); }
+    static QT_HD uint32_t neg(uint32_t a) { return csub(Q - a); }
+    static QT_HD uint32_t half(uint32_t a) { return (a + (Q & (0u - (a & 1u)))) >> 1; }
+};
+
+template <int SET, int RING> struct Nuss {
+    using K = NussCfg<SET>;
+    using O = NussOps<SET, RING>;
+    static constexpr uint32_t M = K::M, R = K::R, LOGM = K::LOGM, ROWS = K::ROWS, Q = K::Q;
+    static constexpr uint32_t EPL = R / 32;  // coefficients per lane in the stage phases (1 or 2)
+
+    static QT_HD uint32_t brev(uint32_t x, uint32_t bits) {
+        uint32_t r = 0;
+        for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+        return r;
+    }
+    // rotation exponent of stage j, group i  (sr of NTT.cu:200-203)
+    static QT_HD uint32_t rot(uint32_t i, uint32_t j) { return (brev(i, LOGM - j) << j) * K::ROT_UNIT; }
+
+    // phase 0: global -> rows (both copies).  tid strides over the n coefficients of polynomial p.
+    static QT_HD void load(uint32_t tid, uint32_t nthreads, const uint32_t* gx, const uint32_t* gy,
+                           uint32_t* sx, uint32_t* sy) {
+        for (uint32_t g = tid; g < K::N; g += nthreads) {
+            const uint32_t i = g % M, j = g / M;
+            const uint32_t vx = gx[g], vy = gy[g];
+            sx[i * K::XS + j] = vx; sx[(i + M) * K::XS + j] = vx;
+            sy[i * K::YS + j] = vy; sy[(i + M) * K::YS + j] = vy;
+        }
+    }
+
+    // forward stage j, one row butterfly bf (0..m-1) of one operand, executed by one warp:
+    // read part (all lanes), then write part.
+    struct Regs { uint32_t t[2], vi[2]; };
+    static QT_HD void fwd_read(uint32_t lane, uint32_t j, uint32_t bf, const uint32_t* v, uint32_t stride, Regs& rg) {
+        const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+        const uint32_t I = (i << (j + 1)) + t, L = I + (1u << j), sr = rot(i, j);
+#pragma unroll
+        for (uint32_t e = 0; e < EPL; e++) {
+            const uint32_t a = lane + 32 * e;
+            const uint32_t src = v[L * stride + ((a - sr) & (R - 1))];
+            rg.t[e] = (a >= sr) ? src : O::neg(src);  // X_l rotated by w^sr (NTT.cu:210-215)
+            rg.vi[e] = v[I * stride + a];
+        }
+    }
+    static QT_HD void fwd_write(uint32_t lane, uint32_t j, uint32_t bf, uint32_t* v, uint32_t stride, const Regs& rg) {
+        const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+        const uint32_t I = (i << (j + 1)) + t, L = I + (1u << j);
+#pragma unroll
+        for (uint32_t e = 0; e < EPL; e++) {
+            const uint32_t a = lane + 32 * e;
+            v[L * stride + a] = O::sub(rg.vi[e], rg.t[e]);  // NTT.cu:217-220
+            v[I * stride + a] = O::add(rg.vi[e], rg.t[e]);
+        }
+    }
+
+    // inverse stage j (0..logm), row butterfly bf, on Z (stored in the X rows)
+    static QT_HD void inv_read(uint32_t lane, uint32_t j, uint32_t bf, const uint32_t* z, Regs& rg) {
+        const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+        const uint32_t A = (i << (j + 1)) + t, B = A + (1u << j);
+#pragma unroll
+        for (uint32_t e = 0; e < EPL; e++) {
+            const uint32_t a = lane + 32 * e;
+            const uint32_t za = z[A * K::XS + a], zb = z[B * K::XS + a];
+            rg.t[e] = O::half(O::sub(za, zb));   // NTT.cu:254-259
+            rg.vi[e] = O::half(O::add(za, zb));
+        }
+    }
+    static QT_HD void inv_write(uint32_t lane, uint32_t j, uint32_t bf, uint32_t* z, const Regs& rg) {
+        const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+        const uint32_t A = (i << (j + 1)) + t, B = A + (1u << j), sr = (j == LOGM) ? 0u : rot(i, j);
+#pragma unroll
+        for (uint32_t e = 0; e < EPL; e++) {
+            const uint32_t a = lane + 32 * e;
+            z[A * K::XS + a] = rg.vi[e];
+            // Z_B[a'] = T[a'+sr] (a' < r-sr) ; = -T[a'-(r-sr)] otherwise   (NTT.cu:262-267)
+            z[B * K::XS + ((a - sr) & (R - 1))] = (a >= sr) ? rg.t[e] : O::neg(rg.t[e]);
+        }
+    }
+
+    // product phase: thread owns row `row` of one polynomial; x, y rows -> z row (written over x)
+    static QT_HD void product(uint32_t* xr /* row of X, becomes Z */, uint32_t* yr /* row of Y */) {
+        if (R == 32) {
+            uint32_t x[32], y[32];
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
+            if (RING == 0) {
+                // naive, NTT.cu:147-165: chain A over j<=k, chain B over j>k, z = A - B
+#pragma unroll
+                for (uint32_t k = 0; k < 32; k++) {
+                    uint32_t A = NussOps<SET, 0>::fold((uint64_t)x[0] * y[k]), B = 0;
+#pragma unroll
+                    for (uint32_t j = 1; j < 32; j++) {
+                        if (j <= k) A = NussOps<SET, 0>::fold((uint64_t)x[j] * y[(k - j) & 31] + A);
+                        else B = NussOps<SET, 0>::fold((uint64_t)x[j] * y[(32 + k - j) & 31] + B);
+                    }
+                    xr[k] = NussOps<SET, 0>::sub(A, B);
+                }
+            } else {
+                uint32_t ny[32];
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) ny[j] = Q - y[j];  // wrapped terms enter negated
+#pragma unroll
+                for (uint32_t k = 0; k < 32; k++) {
+                    uint64_t acc0 = 0, acc1 = 0;  // 16 terms each: 16*q^2 < 2^64 even for the 30-bit q
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++) {
+                        const uint32_t yy = (j <= k) ? y[(k - j) & 31] : ny[(32 + k - j) & 31];
+                        if (j < 16) acc0 += (uint64_t)x[j] * yy;
+                        else acc1 += (uint64_t)x[j] * yy;
+                    }
+                    xr[k] = (uint32_t)((acc0 % Q + acc1 % Q) % Q);
+                }
+            }
+        } else {  // R == 64, Z_q only: y row doubled in place [q - y | y], x in registers
+            uint32_t x[64];
+#pragma unroll
+            for (uint32_t j = 0; j < 64; j++) x[j] = xr[j];
+            for (uint32_t j = 0; j < 64; j++) { const uint32_t v = yr[j]; yr[64 + j] = v; yr[j] = Q - v; }
+            for (uint32_t k = 0; k < 64; k++) {
+                uint64_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (uint32_t j = 0; j < 64; j++) acc[j >> 4] += (uint64_t)x[j] * yr[64 + k - j];
+                xr[k] = (uint32_t)((acc[0] % Q + acc[1] % Q + acc[2] % Q + acc[3] % Q) % Q);
+            }
+        }
+    }
+
+    // final phase: recombination and coalesced store (NTT.cu:271-276)
+    static QT_HD void store(uint32_t tid, uint32_t nthreads, const uint32_t* z, uint32_t* gz) {
+        for (uint32_t g = tid; g < K::N; g += nthreads) {
+            const uint32_t i = g % M, j = g / M;
+            uint32_t v;
+            if (j == 0) v = O::sub(z[i * K::XS], z[(M + i) * K::XS + R - 1]);
+            else v = O::add(z[i * K::XS + j], z[(M + i) * K::XS + j - 1]);
+            gz[g] = v;
+        }
+    }
+};
+
+#if defined(__CUDACC__)
+
+template <int SET, int RING>
+__global__ void __launch_bounds__(NussCfg<SET>::THREADS)
+k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    using K = NussCfg<SET>;
+    using NU = Nuss<SET, RING>;
+    extern __shared__ uint4 nuss_smem_raw[];
+    uint32_t* smem = reinterpret_cast<uint32_t*>(nuss_smem_raw);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t WARPS = K::THREADS / 32;
+    const size_t ngroups = (batch + K::P - 1) / K::P;
+    for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const size_t p0 = grp * K::P;
+        const uint32_t np = (uint32_t)((batch - p0 < K::P) ? batch - p0 : K::P);
+        // load: the threads of the CTA are split evenly over the polynomials of the group
+        {
+            const uint32_t per = K::THREADS / K::P, p = tid / per;
+            if (p < np)
+                NU::load(tid % per, per, x + (p0 + p) * K::N, y + (p0 + p) * K::N, smem + p * K::POLY_WORDS,
+                         smem + p * K::POLY_WORDS + K::X_WORDS);
+        }
+        __syncthreads();
+        // forward stages: P polys x 2 operands x m row butterflies per stage, one warp each
+        for (int j = (int)K::LOGM - 1; j >= 0; j--) {
+            for (uint32_t w = warp; w < K::P * 2 * K::M; w += WARPS) {
+                const uint32_t p = w / (2 * K::M), op = (w / K::M) & 1, bf = w % K::M;
+                if (p >= np) continue;
+                uint32_t* v = smem + p * K::POLY_WORDS + (op ? K::X_WORDS : 0);
+                const uint32_t stride = op ? K::YS : K::XS;
+                typename NU::Regs rg;
+                NU::fwd_read(lane, (uint32_t)j, bf, v, stride, rg);
+                __syncwarp();
+                NU::fwd_write(lane, (uint32_t)j, bf, v, stride, rg);
+            }
+            __syncthreads();
+        }
+        // products: one thread per row
+        {
+            const uint32_t p = tid / K::ROWS, row = tid % K::ROWS;
+            if (p < np)
+                NU::product(smem + p * K::POLY_WORDS + row * K::XS, smem + p * K::POLY_WORDS + K::X_WORDS + row * K::YS);
+        }
+        __syncthreads();
+        // inverse stages on Z (in the X rows)
+        for (uint32_t j = 0; j <= K::LOGM; j++) {
+            for (uint32_t w = warp; w < K::P * K::M; w += WARPS) {
+                const uint32_t p = w / K::M, bf = w % K::M;
+                if (p >= np) continue;
+                uint32_t* zr = smem + p * K::POLY_WORDS;
+                typename NU::Regs rg;
+                NU::inv_read(lane, j, bf, zr, rg);
+                __syncwarp();
+                NU::inv_write(lane, j, bf, zr, rg);
+            }
+            __syncthreads();
+        }
+        {
+            const uint32_t per = K::THREADS / K::P, p = tid / per;
+            if (p < np) NU::store(tid % per, per, smem + p * K::POLY_WORDS, z + (p0 + p) * K::N);
+        }
+        __syncthreads();
+    }
 }
+
+template <int SET> int nuss_setup(int num_sms, int* grid) {
+    using K = NussCfg<SET>;
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_nussbaumer<SET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nussbaumer<SET, 1>, K::THREADS, K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    if (K::R == 32) {
+        int occ0 = 0;
+        e = cudaFuncSetAttribute(k_nussbaumer<SET, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k_nussbaumer<SET, 0>, K::THREADS, K::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        occ = occ0 < occ ? occ0 : occ;
+    }
+    *grid = (occ < 1 ? 1 : occ) * num_sms;
+    return 0;
+}
+
+template <int SET>
+int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring, cudaStream_t s) {
+    using K = NussCfg<SET>;
+    const size_t groups = (batch + K::P - 1) / K::P;
+    const int grid = (int)(groups < (size_t)max_grid ? groups : (size_t)max_grid);
+    if (ring == 0) {
+        if (K::R != 32) return -4;  // ring 2^32-1 is provided for the 32-column splits (n=512, 1024) only
+        if constexpr (K::R == 32)
+            k_nussbaumer<SET, 0><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+    } else {
+        k_nussbaumer<SET, 1><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+    }
+    return (int)cudaGetLastError();
+}
+
+#endif  // __CUDACC__
+
+}  // namespace qt
