@@ -215,6 +215,8 @@ def main():
     ap.add_argument("--set", default="III", choices=list(SETS))
     ap.add_argument("--batch", type=int, default=0, help="polynomials per GPU per step (default: BASELINE config)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other parameter sets / CPU baseline")
+    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2],
+                    help="fused-kernel data path: 0 automatic, 1 direct coalesced loads, 2 TMA-staged")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -254,9 +256,11 @@ def main():
     peaks, peaks_src = load_peaks()
     stream = torch.cuda.Stream(device=dev)
 
-    def run_config(set_id, batch, steps, warmup, sampler=None):
+    def run_config(set_id, batch, steps, warmup, sampler=None, variant=None, nuss_ring=None):
         eng = qt.Engine(set_id, local_rank)
         eng.set_stream(stream.cuda_stream)
+        eng.set_fused_variant(args.variant if variant is None else variant)
+        step = (lambda: eng.polymul(x, y, z, batch)) if nuss_ring is None else (lambda: eng.nussbaumer(x, y, z, nuss_ring, batch))
         p = eng.params
         words = batch * p.n
         x = torch.empty(words, dtype=torch.int32, device=dev)
@@ -267,7 +271,7 @@ def main():
             eng.fill_uniform(x, 1, first)
             eng.fill_uniform(y, 2, first)
             for _ in range(warmup):
-                eng.polymul(x, y, z, batch)
+                step()
         stream.synchronize()
         l0 = eng.launch_count()
         e0 = torch.cuda.Event(enable_timing=True)
@@ -277,7 +281,7 @@ def main():
         with torch.cuda.stream(stream):
             e0.record(stream)
             for _ in range(steps):
-                eng.polymul(x, y, z, batch)
+                step()
             e1.record(stream)
         while not e1.query():  # launches are asynchronous: sample clocks while the GPU works
             if sampler is not None:
@@ -358,6 +362,23 @@ def main():
             extras.append({"param_set": name, "n": int(e2.params.n), "batch": DEFAULT_BATCH[sid], "value": r2, "unit": UNIT,
                            "hbm_frac": r2 * b2 / 1e9 / float(peaks["hbm_gbs"]), "int_frac": r2 * i2 / int_peak})
             e2.close()
+        st = max(3, min(args.steps, 50))
+        variants = {}
+        for vname, v in (("direct_loads", 1), ("tma_staged", 2)):
+            try:
+                e2, _, ms2, _ = run_config(set_id, batch, st, 3, variant=v)
+                variants[vname] = batch * st / (ms2 * 1e-3)
+                e2.close()
+            except Exception as ex:  # e.g. variant unsupported for this shape
+                variants[vname] = str(ex)
+        nuss = {}
+        for rname, ring in (("ring_2p32m1", qt.RING_2P32M1), ("mod_q", qt.RING_MODQ)):
+            try:
+                e2, _, ms2, _ = run_config(set_id, batch, max(3, min(args.steps, 10)), 3, nuss_ring=ring)
+                nuss[rname] = batch * max(3, min(args.steps, 10)) / (ms2 * 1e-3)
+                e2.close()
+            except Exception as ex:
+                nuss[rname] = str(ex)
         from oracle_lib import Oracle
         cpu = cpu_baseline(set_id, Oracle())
 
@@ -390,6 +411,8 @@ def main():
             line["cpu_baseline"] = cpu
         if extras:
             line["other_configs"] = extras
+            line["fused_variants"] = variants
+            line["nussbaumer"] = nuss
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -24,6 +24,10 @@ TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX];
 
 using namespace qt;
 
+#ifndef QT_AUTO_PREFERS_TMA
+#define QT_AUTO_PREFERS_TMA 1
+#endif
+
 #define QT_CUDA(call)                                \
     do {                                             \
         cudaError_t e__ = (call);                    \
@@ -36,12 +40,12 @@ struct qt_ctx {
     RtParams p{};
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    TwQuad* d_lane_fwd = nullptr;
-    TwQuad* d_lane_inv = nullptr;
+    TwQuad* d_lane_fwd = nullptr;  // merged-psi per-lane twiddles; the inverse reads it mirrored
     int num_sms = 0;
-    int grid_fused = 0, grid_fwd = 0, grid_inv = 0, grid_nuss = 0;
-    int occ_fused = 0;
-    size_t smem_fused = 0, smem_one = 0;
+    int grid_fused = 0, grid_fwd = 0, grid_inv = 0, grid_nuss = 0, grid_tma = 0;
+    int occ_fused = 0, occ_tma = 0, tma_warps = 0;
+    int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged
+    size_t smem_fused = 0, smem_one = 0, smem_tma = 0;
     uint64_t launches = 0;
     // host pipeline (qt_polymul_host): lazily created
     static constexpr int PIPE = 3;
@@ -68,19 +72,30 @@ bool g_uni_uploaded[64][NUM_SETS];  // per device
 
 template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
     using S = KernelShape<SET>;
-    c->smem_fused = S::SMEM_FUSED;
-    c->smem_one = S::SMEM_ONE;
-    QT_CUDA(cudaFuncSetAttribute(k_polymul<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_FUSED));
-    QT_CUDA(cudaFuncSetAttribute(k_ntt_forward<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_ONE));
-    QT_CUDA(cudaFuncSetAttribute(k_ntt_inverse<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_ONE));
+    c->smem_fused = S::SMEM_DIRECT;
+    c->smem_one = S::SMEM_DIRECT;
+    QT_CUDA(cudaFuncSetAttribute(k_polymul<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
+    QT_CUDA(cudaFuncSetAttribute(k_ntt_forward<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
+    QT_CUDA(cudaFuncSetAttribute(k_ntt_inverse<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
     int occ = 0;
-    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polymul<SET>, WARPS_PER_CTA * 32, S::SMEM_FUSED));
+    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polymul<SET>, WARPS_PER_CTA * 32, S::SMEM_DIRECT));
     if (occ < 1) return QT_ERR_UNSUPPORTED;
     c->occ_fused = occ;
     c->grid_fused = occ * c->num_sms;
-    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_forward<SET>, WARPS_PER_CTA * 32, S::SMEM_ONE));
+    c->smem_tma = StageShape<SET>::SMEM;
+    c->tma_warps = TmaCfg<SET>::WARPS;
+    c->occ_tma = 0;
+    if (cudaFuncSetAttribute(k_polymul_tma<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM) == cudaSuccess) {
+        int o2 = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_polymul_tma<SET>, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM) == cudaSuccess)
+            c->occ_tma = o2;
+    } else {
+        (void)cudaGetLastError();
+    }
+    c->grid_tma = c->occ_tma * c->num_sms;
+    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_forward<SET>, WARPS_PER_CTA * 32, S::SMEM_DIRECT));
     c->grid_fwd = std::max(1, occ) * c->num_sms;
-    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_inverse<SET>, WARPS_PER_CTA * 32, S::SMEM_ONE));
+    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_inverse<SET>, WARPS_PER_CTA * 32, S::SMEM_DIRECT));
     c->grid_inv = std::max(1, occ) * c->num_sms;
     int rc = nuss_setup<SET>(c->num_sms, &c->grid_nuss);
     if (rc) return rc;
@@ -93,9 +108,7 @@ int upload_tables(qt_ctx* c) {
     build_tables(c->set, &T);
     const size_t quads = T.lane_fwd.size();
     QT_CUDA(cudaMalloc(&c->d_lane_fwd, quads * sizeof(TwQuad)));
-    QT_CUDA(cudaMalloc(&c->d_lane_inv, quads * sizeof(TwQuad)));
     QT_CUDA(cudaMemcpy(c->d_lane_fwd, T.lane_fwd.data(), quads * sizeof(TwQuad), cudaMemcpyHostToDevice));
-    QT_CUDA(cudaMemcpy(c->d_lane_inv, T.lane_inv.data(), quads * sizeof(TwQuad), cudaMemcpyHostToDevice));
     {
         std::lock_guard<std::mutex> lk(g_uni_mutex);
         memcpy(h_uni[c->set], T.uni, sizeof(T.uni));
@@ -122,8 +135,15 @@ inline int grid_for(int max_grid, size_t tiles) {
 template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B,
                                       cudaStream_t s) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
-    k_polymul<SET><<<grid_for(c->grid_fused, tiles), WARPS_PER_CTA * 32, c->smem_fused, s>>>(
-        x, y, z, B, c->d_lane_fwd, c->d_lane_inv);
+    const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;  // bulk copies need 16-byte alignment
+    const bool tma = c->occ_tma > 0 && aligned && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
+    if (tma)
+        k_polymul_tma<SET><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS)),
+                             TmaCfg<SET>::WARPS * 32, c->smem_tma, s>>>(
+            x, y, z, B, c->d_lane_fwd);
+    else
+        k_polymul<SET><<<grid_for(c->grid_fused, tiles), WARPS_PER_CTA * 32, c->smem_fused, s>>>(
+            x, y, z, B, c->d_lane_fwd);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -135,7 +155,7 @@ template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
 }
 template <int SET> int launch_inverse(qt_ctx* c, uint32_t* a, size_t B) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
-    k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_inv);
+    k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_fwd);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -256,7 +276,6 @@ int qt_destroy(qt_ctx* c) {
         if (c->pipe_stream[i]) cudaStreamDestroy(c->pipe_stream[i]);
     }
     if (c->d_lane_fwd) cudaFree(c->d_lane_fwd);
-    if (c->d_lane_inv) cudaFree(c->d_lane_inv);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -265,6 +284,13 @@ int qt_destroy(qt_ctx* c) {
 int qt_set_stream(qt_ctx* c, void* s) {
     if (!c) return QT_ERR_BAD_ARG;
     c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int qt_set_fused_variant(qt_ctx* c, int variant) {
+    if (!c || variant < 0 || variant > 2) return QT_ERR_BAD_ARG;
+    if (variant == 2 && c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
+    c->variant = variant;
     return 0;
 }
 
@@ -432,10 +458,11 @@ int qt_launch_count(qt_ctx* c, uint64_t* out) {
 
 int qt_kernel_info(qt_ctx* c, int* grid, int* block, int* smem, int* per_sm, int* sms) {
     if (!c) return QT_ERR_BAD_ARG;
-    if (grid) *grid = c->grid_fused;
-    if (block) *block = WARPS_PER_CTA * 32;
-    if (smem) *smem = (int)c->smem_fused;
-    if (per_sm) *per_sm = c->occ_fused;
+    const bool tma = c->occ_tma > 0 && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
+    if (grid) *grid = tma ? c->grid_tma : c->grid_fused;
+    if (block) *block = (tma ? c->tma_warps : WARPS_PER_CTA) * 32;
+    if (smem) *smem = (int)(tma ? c->smem_tma : c->smem_fused);
+    if (per_sm) *per_sm = tma ? c->occ_tma : c->occ_fused;
     if (sms) *sms = c->num_sms;
     return 0;
 }

@@ -10,15 +10,31 @@
 
 namespace qt {
 
-constexpr int WARPS_PER_CTA = 8;
+constexpr int WARPS_PER_CTA = 8;   // direct-load kernels
+// Geometry of the TMA-staged fused kernel, chosen by measurement on B200 (tools/ab.py):
+// ONE 16-warp CTA per SM beat 2x8, 3x8, 2x12 and 5x4 warps (221 vs 208-215 M polymul/s at n=1024).
+#ifndef QT_TMA_WARPS
+#define QT_TMA_WARPS 16            // warps per CTA (32 coefficients per thread)
+#endif
+#ifndef QT_TMA_WARPS_E64
+#define QT_TMA_WARPS_E64 12        // n=2048 (64 coefficients per thread): 16 KB of staging per warp
+#endif
+#ifndef QT_TMA_MINB
+#define QT_TMA_MINB 1              // resident CTAs per SM the kernel is compiled for (register budget)
+#endif
+
+// launch geometry of the TMA-staged fused kernel per parameter set
+template <int SET> struct TmaCfg {
+    static constexpr int WARPS = (Cfg<SET>::E == 64) ? QT_TMA_WARPS_E64 : QT_TMA_WARPS;
+    static constexpr int MINB = (Cfg<SET>::E == 64) ? 1 : QT_TMA_MINB;  // 64 coefficients per thread need the registers
+};
 
 template <int SET> struct KernelShape {
     using T = Tile<SET>;
-    static constexpr size_t TW_QUADS = (size_t)T::SLOT_PAIRS * T::BLOCKS;  // per direction
+    static constexpr size_t TW_QUADS = (size_t)T::SLOT_PAIRS * T::BLOCKS;  // one table serves both directions
     static constexpr size_t TW_BYTES = TW_QUADS * sizeof(TwQuad);
     static constexpr size_t BUF_BYTES = (size_t)WARPS_PER_CTA * T::C::TILE_WORDS * sizeof(uint32_t);
-    static constexpr size_t SMEM_FUSED = 2 * TW_BYTES + BUF_BYTES;
-    static constexpr size_t SMEM_ONE = TW_BYTES + BUF_BYTES;
+    static constexpr size_t SMEM_DIRECT = TW_BYTES + BUF_BYTES;
 };
 
 __device__ __forceinline__ void copy_table_to_smem(TwQuad* dst, const TwQuad* __restrict__ src, size_t quads) {
@@ -28,25 +44,23 @@ __device__ __forceinline__ void copy_table_to_smem(TwQuad* dst, const TwQuad* __
 }
 
 // z = x*y mod (X^n+1, q): forward(x), forward(y), pointwise, inverse — one launch, HBM touched
-// once per operand (12n bytes per product).
+// once per operand (12n bytes per product).  Direct-load variant: coalesced LDG/STG, both operands
+// in registers.  Used when the operands are not 16-byte aligned (the TMA variant needs that).
 template <int SET>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
-          const TwQuad* __restrict__ g_lane_fwd, const TwQuad* __restrict__ g_lane_inv) {
+k_polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwQuad* __restrict__ g_lane) {
     using T = Tile<SET>;
     using S = KernelShape<SET>;
     extern __shared__ uint4 smem_raw[];
-    TwQuad* s_fwd = reinterpret_cast<TwQuad*>(smem_raw);
-    TwQuad* s_inv = s_fwd + S::TW_QUADS;
-    uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_inv + S::TW_QUADS);
-    copy_table_to_smem(s_fwd, g_lane_fwd, S::TW_QUADS);
-    copy_table_to_smem(s_inv, g_lane_inv, S::TW_QUADS);
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
-    const TwQuad* tw_f = s_fwd + (lane % T::BLOCKS);
-    const TwQuad* tw_i = s_inv + (lane % T::BLOCKS);
+    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
+    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
 
     for (size_t tile = (size_t)blockIdx.x * WARPS_PER_CTA + warp; tile < ntiles;
@@ -79,20 +93,155 @@ k_polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
     }
 }
 
+// ---- TMA-staged variant (the default) ------------------------------------------------------------
+// Same arithmetic.  Each warp owns two shared-memory buffers A and B of one tile each and two
+// mbarriers.  The operands of the warp's NEXT tile are fetched by 1-D bulk copies (cp.async.bulk =
+// the TMA unit, SASS UBLKCP) that complete on the mbarriers while the current tile is computed, so
+// no register is tied up by a load in flight and the HBM latency is off the critical path.  The
+// buffers are recycled within a tile:
+//     A: x staging -> transposition scratch of x -> stash of NTT(x)      -> (free) next x
+//     B: y staging -> transposition scratch of y and of the inverse pass -> (free) next y
+// so a warp needs 2 tiles of shared memory and ~E+temporaries registers, which is what lets three
+// 8-warp CTAs (24 warps) share an SM.  The two forward transforms run through ONE copy of the code
+// (a 2-trip loop), halving the instruction-cache footprint.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni QT_DONE;\n"
+        "bra.uni QT_WAIT;\n"
+        "QT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// generic-proxy accesses of this thread are ordered before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int SET> struct StageShape {
+    using T = Tile<SET>;
+    static constexpr uint32_t PAD = (T::PPW == 2) ? 16 : 0;  // de-conflicts the rows of the two polynomials
+    static constexpr uint32_t POLY_STRIDE = T::N + PAD;      // words
+    static constexpr uint32_t WORDS = T::PPW * POLY_STRIDE;  // one buffer (>= TILE_WORDS)
+    static constexpr size_t SMEM = KernelShape<SET>::TW_BYTES + (size_t)TmaCfg<SET>::WARPS * 2 * WORDS * sizeof(uint32_t) +
+                                   (size_t)TmaCfg<SET>::WARPS * 2 * sizeof(uint64_t);
+    static __device__ __forceinline__ uint32_t off(uint32_t lane, uint32_t r) {
+        return (lane / T::LPP) * POLY_STRIDE + (lane % T::LPP) + T::LPP * r;
+    }
+};
+
+template <int SET>
+__global__ void __launch_bounds__(TmaCfg<SET>::WARPS * 32, TmaCfg<SET>::MINB)
+k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwQuad* __restrict__ g_lane) {
+    using T = Tile<SET>;
+    using S = KernelShape<SET>;
+    using G = StageShape<SET>;
+    extern __shared__ uint4 smem_raw[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
+    constexpr int NW = TmaCfg<SET>::WARPS;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* A = s_stage + warp * 2 * G::WORDS;
+    uint32_t* B = A + G::WORDS;
+    uint64_t* bar_a = s_bar + 2 * warp;
+    uint64_t* bar_b = bar_a + 1;
+    const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+    const size_t stride = (size_t)gridDim.x * NW;
+    size_t tile = (size_t)blockIdx.x * NW + warp;
+
+    auto issue = [&](const uint32_t* g, uint32_t* st, uint64_t* bar, size_t t) {  // one lane
+        const size_t p0 = t * T::PPW;
+        const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);
+        mbar_expect_tx(bar, np * T::N * (uint32_t)sizeof(uint32_t));
+        if (G::PAD == 0) {
+            bulk_g2s(st, g + p0 * T::N, np * T::N * (uint32_t)sizeof(uint32_t), bar);
+        } else {
+            for (uint32_t p = 0; p < np; p++)
+                bulk_g2s(st + p * G::POLY_STRIDE, g + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar);
+        }
+    };
+
+    if (lane == 0) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        if (tile < ntiles) {
+            issue(x, A, bar_a, tile);
+            issue(y, B, bar_b, tile);
+        }
+    }
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    __syncthreads();
+
+    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
+    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    uint32_t phase = 0;
+    for (; tile < ntiles; tile += stride, phase ^= 1) {
+        const size_t base = tile * T::C::TILE_WORDS;
+        const bool valid = tile * T::PPW + lane / T::LPP < batch;
+        const bool more = tile + stride < ntiles;
+        uint32_t v[T::E];
+#pragma unroll 1
+        for (int op = 0; op < 2; op++) {  // one copy of the forward-transform code for x and y
+            uint32_t* st = op ? B : A;
+            mbar_wait(op ? bar_b : bar_a, phase);
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) v[r] = st[G::off(lane, r)];
+            __syncwarp();
+            T::fwd_rows(v);
+            T::sts_rows(v, st, lane);
+            __syncwarp();
+            T::lds_cols(v, st, lane);
+            T::fwd_cols(v, tw_f);
+            if (op == 0) {
+                __syncwarp();             // every lane has read its columns before A is overwritten
+                T::sts_cols(v, A, lane);  // stash NTT(x); each lane reads back only what it wrote
+            }
+        }
+        T::pointwise_mont_stash(v, A, lane);
+        fence_proxy_async();
+        __syncwarp();                     // A is free: fetch the next tile's x into it
+        if (more && lane == 0) issue(x, A, bar_a, tile + stride);
+        T::inv_cols(v, tw_i);
+        T::sts_cols(v, B, lane);          // (all lanes passed the __syncwarp above after reading B)
+        __syncwarp();
+        T::lds_rows(v, B, lane);
+        fence_proxy_async();
+        __syncwarp();                     // B is free: fetch the next tile's y into it
+        if (more && lane == 0) issue(y, B, bar_b, tile + stride);
+        T::template inv_rows<UNI_INV_FUSED>(v);
+        T::store_rows(v, z + base, lane, valid);
+    }
+}
+
 // forward NTT in place: natural -> NTT domain (bit-reversed, psi merged), canonical
 template <int SET>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_ntt_forward(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane_fwd) {
+k_ntt_forward(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     using T = Tile<SET>;
     using S = KernelShape<SET>;
     extern __shared__ uint4 smem_raw[];
-    TwQuad* s_fwd = reinterpret_cast<TwQuad*>(smem_raw);
-    uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_fwd + S::TW_QUADS);
-    copy_table_to_smem(s_fwd, g_lane_fwd, S::TW_QUADS);
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
-    const TwQuad* tw_f = s_fwd + (lane % T::BLOCKS);
+    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     for (size_t tile = (size_t)blockIdx.x * WARPS_PER_CTA + warp; tile < ntiles;
          tile += (size_t)gridDim.x * WARPS_PER_CTA) {
@@ -118,17 +267,17 @@ k_ntt_forward(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane_fwd) 
 // inverse NTT in place: NTT domain -> natural, n^-1 psi^-i included, canonical
 template <int SET>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane_inv) {
+k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     using T = Tile<SET>;
     using S = KernelShape<SET>;
     extern __shared__ uint4 smem_raw[];
-    TwQuad* s_inv = reinterpret_cast<TwQuad*>(smem_raw);
-    uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_inv + S::TW_QUADS);
-    copy_table_to_smem(s_inv, g_lane_inv, S::TW_QUADS);
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
-    const TwQuad* tw_i = s_inv + (lane % T::BLOCKS);
+    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     for (size_t tile = (size_t)blockIdx.x * WARPS_PER_CTA + warp; tile < ntiles;
          tile += (size_t)gridDim.x * WARPS_PER_CTA) {

@@ -27,7 +27,7 @@ struct HostTables {
     // for the inverse kinds index 0 holds the output scale K and index 1 is pre-multiplied by K
     TwPair uni[UNI_KINDS][UNI_MAX];
     // per-lane twiddles of the contiguous pass: [pair][block], block = n/E lanes
-    std::vector<TwQuad> lane_fwd, lane_inv;
+    std::vector<TwQuad> lane_fwd;  // the inverse pass reads the same table mirrored (qt_tile.cuh inv_cols)
     uint32_t lane_blocks;  // n / E
 };
 
@@ -71,18 +71,16 @@ inline void build_tables(int set, HostTables* T) {
     const uint32_t blocks = n / p.E;
     T->lane_blocks = blocks;
     T->lane_fwd.assign((size_t)p.slot_pairs * blocks, TwQuad{0, 0, 0, 0});
-    T->lane_inv.assign((size_t)p.slot_pairs * blocks, TwQuad{0, 0, 0, 0});
     for (uint32_t jb = 0; jb < blocks; jb++) {
         uint32_t slot = 0;
         for (uint32_t l = p.lb1; l < p.logn; l++) {
             const uint32_t G = p.E >> (p.logn - l);
             for (uint32_t g = 0; g < G; g++, slot++) {
                 const uint32_t k = (1u << l) + jb * G + g;
-                const uint32_t f = zf(k), iv = zi(k);
+                const uint32_t f = zf(k);
                 TwQuad& qf = T->lane_fwd[(size_t)(slot / 2) * blocks + jb];
-                TwQuad& qi = T->lane_inv[(size_t)(slot / 2) * blocks + jb];
-                if (slot & 1) { qf.w1 = f; qf.ws1 = shoup(f, q); qi.w1 = iv; qi.ws1 = shoup(iv, q); }
-                else          { qf.w0 = f; qf.ws0 = shoup(f, q); qi.w0 = iv; qi.ws0 = shoup(iv, q); }
+                if (slot & 1) { qf.w1 = f; qf.ws1 = shoup(f, q); }
+                else          { qf.w0 = f; qf.ws0 = shoup(f, q); }
             }
         }
     }

@@ -163,7 +163,10 @@ template <int SET> struct Tile {
     }
 
     // cols layout, inverse levels LOGN-1..LB1; inputs < 2q.  Ends with the mid-transform fold.
-    static QT_HD void inv_cols(uint32_t (&v)[E], const TwQuad* tw) {
+    // No inverse table: zeta[k]^-1 = -zeta[k'] with k' the mirror of k inside its level
+    // (psi^-e = -psi^(n-e)), so (a-b)*zeta^-1 = (b-a)*zeta[k'].  The mirror of lane-block j, group g
+    // is lane-block BLOCKS-1-j, group G-1-g: `tw_mirror` = &lane_fwd[BLOCKS-1-block].
+    static QT_HD void inv_cols(uint32_t (&v)[E], const TwQuad* tw_mirror) {
 #pragma unroll
         for (uint32_t k = 0; k < LB2; k++) {
             const uint32_t half = 1u << k;
@@ -172,7 +175,12 @@ template <int SET> struct Tile {
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t g = i / half, j = i % half;
-                gs(v[2 * g * half + j], v[2 * g * half + j + half], lane_slot(tw, G - G0 + g), bound);
+                uint32_t& a = v[2 * g * half + j];
+                uint32_t& b = v[2 * g * half + j + half];
+                const TwPair t = lane_slot(tw_mirror, G - G0 + (G - 1 - g));
+                const uint32_t s_ = a + b, d = b - a + bound * Q;
+                a = LAZY ? s_ : csub(s_, TWO_Q);
+                b = mul_shoup(d, t);
             }
         }
         if (LAZY) {
@@ -212,6 +220,20 @@ template <int SET> struct Tile {
         for (uint32_t r = 0; r < E; r++) {
             if (LAZY) a[r] = mul_mont(a[r], b[r]);
             else a[r] = mul_mont(csub(a[r], TWO_Q), csub(b[r], TWO_Q));
+        }
+    }
+
+    // same, the second operand read back from a stash written with sts_cols (keeps it out of registers)
+    static QT_HD void pointwise_mont_stash(uint32_t (&a)[E], const uint32_t* stash, uint32_t lane) {
+#pragma unroll
+        for (uint32_t c = 0; c < E / 4; c++) {
+            const U4 u = *reinterpret_cast<const U4*>(stash + swz(E * lane + 4 * c));
+            const uint32_t b[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                if (LAZY) a[4 * c + k] = mul_mont(a[4 * c + k], b[k]);
+                else a[4 * c + k] = mul_mont(csub(a[4 * c + k], TWO_Q), csub(b[k], TWO_Q));
+            }
         }
     }
 

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libqtesla_b200.so")
+LIB_PATH = os.environ.get("QT_LIB_PATH") or os.path.join(PKG_DIR, "libqtesla_b200.so")  # override: A/B builds
 
 SET_I, SET_III, SET_P_I, SET_P_III = 0, 1, 2, 3
 SET_NAMES = {SET_I: "qTESLA-I", SET_III: "qTESLA-III", SET_P_I: "qTESLA-p-I", SET_P_III: "qTESLA-p-III"}
@@ -39,6 +39,7 @@ _SIGNATURES = {
     "qt_destroy": (C.c_int, [_vp]),
     "qt_set_stream": (C.c_int, [_vp, _vp]),
     "qt_synchronize": (C.c_int, [_vp]),
+    "qt_set_fused_variant": (C.c_int, [_vp, C.c_int]),
     "qt_device_malloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "qt_device_free": (C.c_int, [_vp, _vp]),
     "qt_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
@@ -154,6 +155,10 @@ class Engine:
     # -- plumbing
     def set_stream(self, cuda_stream):
         _check(lib().qt_set_stream(self._h, cuda_stream))
+
+    def set_fused_variant(self, variant):
+        """0 automatic, 1 direct coalesced loads, 2 TMA bulk copies staged through shared memory"""
+        _check(lib().qt_set_fused_variant(self._h, variant))
 
     def synchronize(self):
         _check(lib().qt_synchronize(self._h))

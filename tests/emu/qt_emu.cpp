@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../ntt-gpu-qtesla_b200/csrc/qt_tile.cuh"
+#include "../../ntt-gpu-qtesla_b200/csrc/qt_nussbaumer.cuh"
 
 namespace qt {
 TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX];
@@ -26,7 +27,7 @@ template <int SET> struct Emu {
         memcpy(h_uni[SET], tab.uni, sizeof(tab.uni));
     }
     const TwQuad* twf(uint32_t lane) const { return tab.lane_fwd.data() + lane % T::BLOCKS; }
-    const TwQuad* twi(uint32_t lane) const { return tab.lane_inv.data() + lane % T::BLOCKS; }
+    const TwQuad* twi(uint32_t lane) const { return tab.lane_fwd.data() + (T::BLOCKS - 1 - lane % T::BLOCKS); }
 
     void polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
         alignas(16) static uint32_t buf[64 * 32];
@@ -150,6 +151,60 @@ template <int SET> Emu<SET>& emu() {
 
 }  // namespace
 
+// Nussbaumer: same phase sequence as k_nussbaumer; warps run read-all-lanes then write-all-lanes,
+// threads of a phase run one after another between the kernel's __syncthreads points.
+template <int SET, int RING> int emu_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    using K = NussCfg<SET>;
+    using NU = Nuss<SET, RING>;
+    if (RING == 0 && K::R != 32) return -4;
+    std::vector<uint32_t> smem(K::P * K::POLY_WORDS);
+    constexpr uint32_t WARPS = K::THREADS / 32;
+    const size_t ngroups = (batch + K::P - 1) / K::P;
+    for (size_t grp = 0; grp < ngroups; grp++) {
+        const size_t p0 = grp * K::P;
+        const uint32_t np = (uint32_t)((batch - p0 < K::P) ? batch - p0 : K::P);
+        const uint32_t per = K::THREADS / K::P;
+        for (uint32_t tid = 0; tid < K::THREADS; tid++) {
+            const uint32_t p = tid / per;
+            if (p < np)
+                NU::load(tid % per, per, x + (p0 + p) * K::N, y + (p0 + p) * K::N, smem.data() + p * K::POLY_WORDS,
+                         smem.data() + p * K::POLY_WORDS + K::X_WORDS);
+        }
+        for (int j = (int)K::LOGM - 1; j >= 0; j--)
+            for (uint32_t warp = 0; warp < WARPS; warp++)
+                for (uint32_t w = warp; w < K::P * 2 * K::M; w += WARPS) {
+                    const uint32_t p = w / (2 * K::M), op = (w / K::M) & 1, bf = w % K::M;
+                    if (p >= np) continue;
+                    uint32_t* v = smem.data() + p * K::POLY_WORDS + (op ? K::X_WORDS : 0);
+                    const uint32_t stride = op ? K::YS : K::XS;
+                    typename NU::Regs rg[32];
+                    for (uint32_t lane = 0; lane < 32; lane++) NU::fwd_read(lane, (uint32_t)j, bf, v, stride, rg[lane]);
+                    for (uint32_t lane = 0; lane < 32; lane++) NU::fwd_write(lane, (uint32_t)j, bf, v, stride, rg[lane]);
+                }
+        for (uint32_t tid = 0; tid < K::THREADS; tid++) {
+            const uint32_t p = tid / K::ROWS, row = tid % K::ROWS;
+            if (p < np)
+                NU::product(smem.data() + p * K::POLY_WORDS + row * K::XS,
+                            smem.data() + p * K::POLY_WORDS + K::X_WORDS + row * K::YS);
+        }
+        for (uint32_t j = 0; j <= K::LOGM; j++)
+            for (uint32_t warp = 0; warp < WARPS; warp++)
+                for (uint32_t w = warp; w < K::P * K::M; w += WARPS) {
+                    const uint32_t p = w / K::M, bf = w % K::M;
+                    if (p >= np) continue;
+                    uint32_t* zr = smem.data() + p * K::POLY_WORDS;
+                    typename NU::Regs rg[32];
+                    for (uint32_t lane = 0; lane < 32; lane++) NU::inv_read(lane, j, bf, zr, rg[lane]);
+                    for (uint32_t lane = 0; lane < 32; lane++) NU::inv_write(lane, j, bf, zr, rg[lane]);
+                }
+        for (uint32_t tid = 0; tid < K::THREADS; tid++) {
+            const uint32_t p = tid / per;
+            if (p < np) NU::store(tid % per, per, smem.data() + p * K::POLY_WORDS, z + (p0 + p) * K::N);
+        }
+    }
+    return 0;
+}
+
 #define EMU_DISPATCH(set, call)                  \
     switch (set) {                               \
     case SET_I: emu<SET_I>().call; break;        \
@@ -171,6 +226,19 @@ int qtemu_forward(int set, uint32_t* a, size_t batch) {
 int qtemu_inverse(int set, uint32_t* a, size_t batch) {
     EMU_DISPATCH(set, inverse(a, batch));
     return 0;
+}
+int qtemu_nussbaumer(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring) {
+    switch (set * 2 + ring) {
+    case 0: return emu_nussbaumer<SET_I, 0>(x, y, z, batch);
+    case 1: return emu_nussbaumer<SET_I, 1>(x, y, z, batch);
+    case 2: return emu_nussbaumer<SET_III, 0>(x, y, z, batch);
+    case 3: return emu_nussbaumer<SET_III, 1>(x, y, z, batch);
+    case 4: return emu_nussbaumer<SET_P_I, 0>(x, y, z, batch);
+    case 5: return emu_nussbaumer<SET_P_I, 1>(x, y, z, batch);
+    case 6: return emu_nussbaumer<SET_P_III, 0>(x, y, z, batch);
+    case 7: return emu_nussbaumer<SET_P_III, 1>(x, y, z, batch);
+    default: return -1;
+    }
 }
 int qtemu_bank_conflicts(int set) {
     int r = 0;

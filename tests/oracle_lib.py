@@ -121,6 +121,8 @@ class Oracle:
         x = np.ascontiguousarray(x, np.uint32)
         y = np.ascontiguousarray(y, np.uint32)
         z = np.empty_like(x)
+        if x.size == 0:
+            return z
         if threads is None:
             assert self.lib.qto_polymul(s, _p(x), _p(y), _p(z), self._B(s, x), variant) == 0
         else:

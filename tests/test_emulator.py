@@ -23,6 +23,7 @@ def emu():
     L.qtemu_polymul.argtypes = [C.c_int, u, u, u, C.c_size_t]
     L.qtemu_forward.argtypes = [C.c_int, u, C.c_size_t]
     L.qtemu_inverse.argtypes = [C.c_int, u, C.c_size_t]
+    L.qtemu_nussbaumer.argtypes = [C.c_int, u, u, u, C.c_size_t, C.c_int]
     return L
 
 
@@ -50,3 +51,27 @@ def test_emulated_kernel_equals_oracle(emu, oracle, s):
 @pytest.mark.parametrize("s", ALL_SETS)
 def test_shared_memory_patterns_conflict_free(emu, s):
     assert emu.qtemu_bank_conflicts(s) == 1
+
+
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_emulated_nussbaumer_equals_oracle(emu, oracle, s):
+    p = oracle.params(s)
+    B = 5
+    rng = np.random.default_rng(10 + s)
+    x = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    y = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    x[: p.n] = p.q - 1
+    y[: p.n] = p.q - 1
+    z = np.zeros_like(x)
+    assert emu.qtemu_nussbaumer(s, _p(x), _p(y), _p(z), B, 1) == 0          # Z_q mode == NTT product
+    assert np.array_equal(z, oracle.polymul(s, x, y))
+    xr = rng.integers(0, 2 ** 32, B * p.n, dtype=np.uint32)
+    yr = rng.integers(0, 2 ** 32, B * p.n, dtype=np.uint32)
+    xr[: p.n] = 1; yr[: p.n] = 1; xr[p.n: 2 * p.n] = 0xFFFFFFFF
+    yr[2 * p.n: 3 * p.n] = 0
+    yr[2 * p.n + rng.choice(p.n, 40, replace=False)] = 0xFFFFFFFE
+    rc = emu.qtemu_nussbaumer(s, _p(xr), _p(yr), _p(z), B, 0)               # ring 2^32-1, bit-exact incl. zeros
+    if p.n == 2048:
+        assert rc == -4   # the 64-column split is provided over Z_q only
+    else:
+        assert rc == 0 and np.array_equal(z, oracle.nussbaumer(p.n, xr, yr))

@@ -33,12 +33,31 @@ def rand_pair(q, words, seed):
     return rng.integers(0, q, words, dtype=np.uint32), rng.integers(0, q, words, dtype=np.uint32)
 
 
+@pytest.mark.parametrize("variant", [1, 2])   # 1 = direct coalesced loads, 2 = TMA bulk copies + mbarrier
 @pytest.mark.parametrize("s", ALL_SETS)
-@pytest.mark.parametrize("B", [1, 2, 3, 67, 1000])
-def test_fused_polymul_equals_oracle(engines, oracle, s, B):
+@pytest.mark.parametrize("B", [1, 2, 3, 67, 1000, 5001])
+def test_fused_polymul_equals_oracle(engines, oracle, s, B, variant):
     eng = engines[s]
-    x, y = rand_pair(eng.q, B * eng.n, 100 * s + B)
-    assert np.array_equal(eng.polymul_np(x, y), oracle.polymul(s, x, y))
+    eng.set_fused_variant(variant)
+    try:
+        x, y = rand_pair(eng.q, B * eng.n, 100 * s + B)
+        assert np.array_equal(eng.polymul_np(x, y), oracle.polymul(s, x, y, threads=0))
+    finally:
+        eng.set_fused_variant(0)
+
+
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_fused_variants_agree_at_full_size(engines, s):
+    import torch
+    eng = engines[s]
+    B = FULL_BATCH[s]
+    x = torch.empty(B * eng.n, dtype=torch.int32, device="cuda")
+    y = torch.empty_like(x); z1 = torch.empty_like(x); z2 = torch.empty_like(x)
+    eng.fill_uniform(x, 1, 7); eng.fill_uniform(y, 2, 7)
+    eng.set_fused_variant(1); eng.polymul(x, y, z1)
+    eng.set_fused_variant(2); eng.polymul(x, y, z2)
+    eng.set_fused_variant(0); eng.synchronize()
+    assert torch.equal(z1, z2)
 
 
 def test_golden_vectors_III(engines, golden):

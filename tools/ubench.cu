@@ -40,6 +40,28 @@ template <int OP> __device__ __forceinline__ void step(uint32_t (&r)[CHAINS], ui
             w[i] = x;
         }
         if (OP == 9) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(r[i]));
+        if (OP == 10) {  // fp64 fma on the accumulator pair
+            double d = __longlong_as_double((long long)w[i]);
+            asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d) : "d"(1.0000001), "d"(0.5));
+            w[i] = (uint64_t)__double_as_longlong(d);
+        }
+        if (OP == 11) {  // fp32 fma
+            float f = __uint_as_float(r[i]);
+            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f));
+            r[i] = __float_as_uint(f);
+        }
+        if (OP == 12) {  // fp64 fma + integer mad.lo interleaved: do the two pipes overlap?
+            double d = __longlong_as_double((long long)w[i]);
+            asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d) : "d"(1.0000001), "d"(0.5));
+            w[i] = (uint64_t)__double_as_longlong(d);
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));
+        }
+        if (OP == 13) {  // mul.hi + fp32 fma interleaved: does FFMA find room beside IMAD.HI?
+            asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
+            float f = __uint_as_float((uint32_t)w[i]);
+            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f));
+            w[i] = __float_as_uint(f);
+        }
     }
 }
 
@@ -98,6 +120,10 @@ int main() {
     run<4>("lop3", 1, p.multiProcessorCount, out, cyc, false);
     run<5>("min_u32", 1, p.multiProcessorCount, out, cyc, false);
     run<9>("shfl_bfly", 1, p.multiProcessorCount, out, cyc, false);
+    run<10>("fma_f64", 1, p.multiProcessorCount, out, cyc, false);
+    run<11>("fma_f32", 1, p.multiProcessorCount, out, cyc, false);
+    run<12>("fma_f64_plus_mad_lo (2 instr)", 2, p.multiProcessorCount, out, cyc, false);
+    run<13>("mul_hi_plus_fma_f32 (2 instr)", 2, p.multiProcessorCount, out, cyc, false);
     run<8>("mad_lo_plus_add (2 instr)", 2, p.multiProcessorCount, out, cyc, false);
     run<7>("shoup_butterfly (5 instr, 3 mul)", 5, p.multiProcessorCount, out, cyc, true);
     printf("}\n");
