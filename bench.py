@@ -247,11 +247,7 @@ def main():
             dist.barrier()
 
     def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return qt.sharding.max_over_ranks(v, dist if world > 1 else None, dev)
 
     peaks, peaks_src = load_peaks()
     stream = torch.cuda.Stream(device=dev)
@@ -266,7 +262,7 @@ def main():
         x = torch.empty(words, dtype=torch.int32, device=dev)
         y = torch.empty(words, dtype=torch.int32, device=dev)
         z = torch.empty(words, dtype=torch.int32, device=dev)
-        first = rank * words  # every rank owns its own slice of the global synthetic stream
+        first = qt.sharding.weak_scaling_slice(batch, p.n, rank)  # this rank's slice of the global synthetic stream
         with torch.cuda.stream(stream):
             eng.fill_uniform(x, 1, first)
             eng.fill_uniform(y, 2, first)

@@ -12,7 +12,8 @@ from .engine import (Engine, QtError, lib, get_params, get_table, device_count, 
                      TABLE_BITREV, TABLE_PHI, TABLE_INVPHI, TABLE_TF0, TABLE_TI0,
                      RING_2P32M1, RING_MODQ, LIB_PATH)
 from . import harness  # noqa: F401
+from . import sharding  # noqa: F401
 
 __all__ = ["Engine", "QtError", "lib", "get_params", "get_table", "device_count", "polymul_host_multi",
-           "SET_I", "SET_III", "SET_P_I", "SET_P_III", "SET_NAMES", "harness", "LIB_PATH",
+           "SET_I", "SET_III", "SET_P_I", "SET_P_III", "SET_NAMES", "harness", "sharding", "LIB_PATH",
            "TABLE_BITREV", "TABLE_PHI", "TABLE_INVPHI", "TABLE_TF0", "TABLE_TI0", "RING_2P32M1", "RING_MODQ"]

@@ -256,3 +256,22 @@ def test_nussbaumer_modq_equals_ntt(engines, oracle, qt, s):
         raise
     eng.synchronize()
     assert np.array_equal(tz.cpu().numpy().view(np.uint32), oracle.polymul(s, x, y))
+
+
+def test_cxx_harness_reference_command_line():
+    """tools/harness/qtesla_harness = the reference's main.cu re-created on the C ABI: the reference's
+    own command line `-speedgpu 3` must print the all-ones known answer."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "tools", "harness")], check=True)
+    exe = os.path.join(root, "tools", "harness", "qtesla_harness")
+    for opt in ("2", "3", "4", "5", "6"):
+        out = subprocess.run([exe, "-speedgpu", opt], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        assert "Multiplications per second" in out.stdout
+        assert "8403971 8403973 8403975" in out.stdout            # z[k] = 2k+2-n mod q, both batch rows
+        assert out.stdout.count("8403971 8403973 8403975") == 2
+    out = subprocess.run([exe, "-speedgpu", "9"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "4294966273 4294966275 4294966277" in out.stdout   # Nussbaumer ring KAT
+    out = subprocess.run([exe, "-speedgpu", "3", "-set", "p-III", "-batch", "3"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and str((2 - 2048) % 856145921) in out.stdout
