@@ -115,6 +115,14 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(seen), "samples": len(mhz)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not the box)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU implementation (oracle/_ref, built from the unmodified
     sources) on all host threads; falls back to the oracle port when _ref was not built."""
@@ -127,7 +135,7 @@ def reference_arm(args, rank, world):
     p = o.params(set_id)
     use_ref = Reference.available() and set_id == 1
     ref = Reference() if use_ref else None
-    threads = ref.max_threads() if use_ref else o.max_threads()
+    threads = host_threads()
     run = (lambda x, y: ref.polymul(x, y, 0, threads)) if use_ref else (lambda x, y: o.polymul(set_id, x, y, threads=threads))
     # calibrate, then size a step so that the whole run lasts ~20 s
     cal = 64 * threads
@@ -177,7 +185,7 @@ def cpu_baseline(set_id, o):
     p = o.params(set_id)
     use_ref = Reference.available() and set_id == 1
     ref = Reference() if use_ref else None
-    threads = ref.max_threads() if use_ref else o.max_threads()
+    threads = host_threads()
     run = (lambda x, y, t: ref.polymul(x, y, 0, t)) if use_ref else (lambda x, y, t: o.polymul(set_id, x, y, threads=t))
     cal = 32 * threads
     x = o.splitmix(1, 0, p.q, cal * p.n)
@@ -391,7 +399,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                          "frac": hbm_achieved / float(peaks["hbm_gbs"]), "traffic": traffic,
-                         "peak_source": peaks_src, "kernel": "k_polymul", "kernel_ms": kernel_ms,
+                         "peak_source": peaks_src, "kernel": "k_polymul_tma" if eng.kernel_info()["block"] != 256 else "k_polymul",
+                         "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_pp * batch,
                          "note": "HBM view; the binding roofline is the integer-multiply pipe, see roofline_int"},
             "roofline_int": {"bound": "int_mul_pipe", "achieved": int_achieved / 1e12, "peak": int_peak / 1e12,
