@@ -267,9 +267,199 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
     }
 }
 
+// ---- warp-resident variant for the 32-column splits (n = 512, 1024) ------------------------------
+// One WARP per polynomial.  Stage phases: lane = coefficient index a (0..31), registers = rows, so
+// every row butterfly is register-to-register, the negacyclic rotation w^sr is ONE warp shuffle with a
+// compile-time lane offset and the sign a lane predicate — no shared memory, no barrier.  Product
+// phase: the rows are transposed through shared memory (stride 33, conflict-free both ways) so that
+// lane = row; each lane multiplies its row(s) privately: 32x32 multiply-accumulates from registers.
+// Z_q mode accumulates 64-bit products lazily and Montgomery-reduces once per accumulator; the common
+// factor 2^-32 is removed by one Shoup multiplication per output coefficient at the very end.
+template <int SET, int RING> struct NussWarp {
+    using K = NussCfg<SET>;
+    using O = NussOps<SET, RING>;
+    using T = Tile<SET>;
+    static constexpr uint32_t M = K::M, LOGM = K::LOGM, ROWS = K::ROWS, Q = K::Q;
+    static constexpr uint32_t RS = 33;                                   // row stride in shared memory
+    static constexpr uint32_t WARP_WORDS = 2 * ROWS * RS;                // X rows then Y rows
+    static constexpr uint32_t WARPS = 8;
+    static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_WORDS * sizeof(uint32_t);
+    static constexpr uint32_t RPL = ROWS / 32;                           // rows per lane in the product phase
+    // terms a 64-bit accumulator may take before a Montgomery reduction: sum < q * 2^32
+    static constexpr uint32_t TERMS = (T::QCAP >= 32) ? 32 : (T::QCAP >= 8 ? 8 : 4);
+
+    static __device__ __forceinline__ uint32_t rot(uint32_t i, uint32_t j) {
+        return (c_bitrev(i, LOGM - j) << j) * K::ROT_UNIT;
+    }
+
+    static __device__ __forceinline__ void forward(uint32_t (&v)[ROWS], uint32_t lane) {
+#pragma unroll
+        for (int j = (int)LOGM - 1; j >= 0; j--) {
+#pragma unroll
+            for (uint32_t bf = 0; bf < M; bf++) {
+                const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+                const uint32_t I = (i << (j + 1)) + t, L = I + (1u << j), sr = rot(i, (uint32_t)j);
+                uint32_t tv = v[L];
+                if (sr != 0) {  // X_l * w^sr: coefficient a comes from a - sr, negated on wrap-around
+                    const uint32_t src = __shfl_sync(0xffffffffu, tv, (lane - sr) & 31u);
+                    tv = (lane >= sr) ? src : O::neg(src);
+                }
+                const uint32_t vi = v[I];
+                v[L] = O::sub(vi, tv);
+                v[I] = O::add(vi, tv);
+            }
+        }
+    }
+
+    static __device__ __forceinline__ void inverse(uint32_t (&z)[ROWS], uint32_t lane) {
+#pragma unroll
+        for (uint32_t j = 0; j <= LOGM; j++) {
+#pragma unroll
+            for (uint32_t bf = 0; bf < M; bf++) {
+                const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+                const uint32_t A = (i << (j + 1)) + t, B = A + (1u << j);
+                const uint32_t sr = (j == LOGM) ? 0u : rot(i, j);
+                const uint32_t za = z[A], zb = z[B];
+                uint32_t tv = O::half(O::sub(za, zb));
+                z[A] = O::half(O::add(za, zb));
+                if (sr != 0) {  // Z_B = T * w^-sr: coefficient a takes T[a + sr], negated on wrap-around
+                    const uint32_t src = __shfl_sync(0xffffffffu, tv, (lane + sr) & 31u);
+                    tv = (lane < 32u - sr) ? src : O::neg(src);
+                }
+                z[B] = tv;
+            }
+        }
+    }
+
+    // one row: z = x (*) y negacyclic, length 32; x, y, z are shared-memory rows (z overwrites x)
+    static __device__ __forceinline__ void product_row(uint32_t* xr, const uint32_t* yr) {
+        uint32_t x[32], y[32];
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
+        if (RING == 0) {
+#pragma unroll
+            for (uint32_t k = 0; k < 32; k++) {  // naive, NTT.cu:147-165: chains A (j<=k) and B (j>k)
+                uint32_t A = NussOps<SET, 0>::fold((uint64_t)x[0] * y[k]), B = 0;
+#pragma unroll
+                for (uint32_t j = 1; j < 32; j++) {
+                    if (j <= k) A = NussOps<SET, 0>::fold((uint64_t)x[j] * y[(k - j) & 31] + A);
+                    else B = NussOps<SET, 0>::fold((uint64_t)x[j] * y[(32 + k - j) & 31] + B);
+                }
+                xr[k] = NussOps<SET, 0>::sub(A, B);
+            }
+        } else {
+            uint32_t ny[32];
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) ny[j] = Q - y[j];  // wrapped terms enter negated
+#pragma unroll
+            for (uint32_t k = 0; k < 32; k++) {
+                uint32_t r = 0;
+#pragma unroll
+                for (uint32_t g = 0; g < 32 / TERMS; g++) {
+                    uint64_t acc = 0;
+#pragma unroll
+                    for (uint32_t jj = 0; jj < TERMS; jj++) {
+                        const uint32_t j = g * TERMS + jj;
+                        acc += (uint64_t)x[j] * ((j <= k) ? y[(k - j) & 31] : ny[(32 + k - j) & 31]);
+                    }
+                    const uint32_t m = (uint32_t)acc * T::C::QINV_NEG;          // Montgomery: acc * 2^-32
+                    const uint32_t red = (uint32_t)((acc + (uint64_t)m * Q) >> 32);  // in [0, 2q)
+                    r = (g == 0) ? red : r + red;
+                }
+                // canonical: r < (32/TERMS)*2q
+                if (32 / TERMS == 1) r = T::csub(r, Q);
+                else r = T::csub(T::fold2q(r), Q);
+                xr[k] = r;
+            }
+        }
+    }
+};
+
+template <int SET, int RING>
+__global__ void __launch_bounds__(NussWarp<SET, RING>::WARPS * 32)
+k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    using W = NussWarp<SET, RING>;
+    using K = NussCfg<SET>;
+    using O = NussOps<SET, RING>;
+    using T = Tile<SET>;
+    static_assert(K::R == 32, "warp-resident Nussbaumer needs 32 columns");
+    extern __shared__ uint4 nuss_smem_raw[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* sx = reinterpret_cast<uint32_t*>(nuss_smem_raw) + warp * W::WARP_WORDS;
+    uint32_t* sy = sx + W::ROWS * W::RS;
+    // 2^32 mod q with its Shoup companion: removes the Montgomery factor of the products
+    const TwPair rfix{T::C::R_MODQ, (uint32_t)(((uint64_t)T::C::R_MODQ << 32) / T::Q)};
+    for (size_t p = (size_t)blockIdx.x * W::WARPS + warp; p < batch; p += (size_t)gridDim.x * W::WARPS) {
+        const uint32_t* gx = x + p * K::N;
+        const uint32_t* gy = y + p * K::N;
+        uint32_t v[W::ROWS];
+#pragma unroll 1
+        for (int op = 0; op < 2; op++) {
+            const uint4* g = reinterpret_cast<const uint4*>((op ? gy : gx) + K::M * lane);  // X_i[a] = x[m*a + i]
+#pragma unroll
+            for (uint32_t c = 0; c < K::M / 4; c++) {
+                const uint4 u = g[c];
+                v[4 * c] = u.x; v[4 * c + 1] = u.y; v[4 * c + 2] = u.z; v[4 * c + 3] = u.w;
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < K::M; i++) v[i + K::M] = v[i];  // rows m..2m-1 are copies (NTT.cu:187-191)
+            W::forward(v, lane);
+            uint32_t* s = op ? sy : sx;
+#pragma unroll
+            for (uint32_t r = 0; r < W::ROWS; r++) s[r * W::RS + lane] = v[r];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t h = 0; h < W::RPL; h++) W::product_row(sx + (lane + 32 * h) * W::RS, sy + (lane + 32 * h) * W::RS);
+        __syncwarp();
+#pragma unroll
+        for (uint32_t r = 0; r < W::ROWS; r++) v[r] = sx[r * W::RS + lane];
+        __syncwarp();
+        W::inverse(v, lane);
+        // recombination (NTT.cu:271-276): z[m*a + i] = Z_i[a] + Z_{m+i}[a-1]; a = 0 wraps with a sign
+        uint4* gz = reinterpret_cast<uint4*>(z + p * K::N + K::M * lane);
+#pragma unroll
+        for (uint32_t c = 0; c < K::M / 4; c++) {
+            uint32_t o[4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t i = 4 * c + k;
+                const uint32_t up = __shfl_sync(0xffffffffu, v[K::M + i], (lane - 1) & 31u);
+                uint32_t r = (lane == 0) ? O::sub(v[i], up) : O::add(v[i], up);
+                if (RING == 1) r = T::csub(T::mul_shoup(r, rfix), T::Q);
+                o[k] = r;
+            }
+            gz[c] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 template <int SET> int nuss_setup(int num_sms, int* grid) {
     using K = NussCfg<SET>;
     cudaError_t e;
+    if constexpr (K::R == 32) {  // warp-resident kernels
+        int occ = 64;
+        {
+            using W = NussWarp<SET, 0>;
+            e = cudaFuncSetAttribute(k_nussbaumer_warp<SET, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM_BYTES);
+            if (e != cudaSuccess) return (int)e;
+            int o = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_nussbaumer_warp<SET, 0>, W::WARPS * 32, W::SMEM_BYTES);
+            if (e != cudaSuccess) return (int)e;
+            occ = o < occ ? o : occ;
+        }
+        {
+            using W = NussWarp<SET, 1>;
+            e = cudaFuncSetAttribute(k_nussbaumer_warp<SET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM_BYTES);
+            if (e != cudaSuccess) return (int)e;
+            int o = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_nussbaumer_warp<SET, 1>, W::WARPS * 32, W::SMEM_BYTES);
+            if (e != cudaSuccess) return (int)e;
+            occ = o < occ ? o : occ;
+        }
+        *grid = (occ < 1 ? 1 : occ) * num_sms;
+        return 0;
+    }
     e = cudaFuncSetAttribute(k_nussbaumer<SET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     int occ = 0;
@@ -290,6 +480,15 @@ template <int SET> int nuss_setup(int num_sms, int* grid) {
 template <int SET>
 int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring, cudaStream_t s) {
     using K = NussCfg<SET>;
+    if constexpr (K::R == 32) {
+        if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15) != 0) return -2;  // 128-bit accesses
+        using W0 = NussWarp<SET, 0>;
+        const size_t ctas = (batch + W0::WARPS - 1) / W0::WARPS;
+        const int g = (int)(ctas < (size_t)max_grid ? ctas : (size_t)max_grid);
+        if (ring == 0) k_nussbaumer_warp<SET, 0><<<g, W0::WARPS * 32, W0::SMEM_BYTES, s>>>(x, y, z, batch);
+        else k_nussbaumer_warp<SET, 1><<<g, NussWarp<SET, 1>::WARPS * 32, NussWarp<SET, 1>::SMEM_BYTES, s>>>(x, y, z, batch);
+        return (int)cudaGetLastError();
+    }
     const size_t groups = (batch + K::P - 1) / K::P;
     const int grid = (int)(groups < (size_t)max_grid ? groups : (size_t)max_grid);
     if (ring == 0) {

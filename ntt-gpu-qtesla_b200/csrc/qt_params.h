@@ -7,14 +7,20 @@
 #pragma once
 #include <cstdint>
 
+#if defined(__CUDACC__)
+#define QT_CHD __host__ __device__ constexpr
+#else
+#define QT_CHD constexpr
+#endif
+
 namespace qt {
 
 enum : int { SET_I = 0, SET_III = 1, SET_P_I = 2, SET_P_III = 3, NUM_SETS = 4 };
 
-constexpr uint32_t c_mulmod(uint32_t a, uint32_t b, uint32_t q) {
+QT_CHD uint32_t c_mulmod(uint32_t a, uint32_t b, uint32_t q) {
     return (uint32_t)((uint64_t)a * b % q);
 }
-constexpr uint32_t c_powmod(uint32_t b, uint64_t e, uint32_t q) {
+QT_CHD uint32_t c_powmod(uint32_t b, uint64_t e, uint32_t q) {
     uint64_t r = 1, x = b % q;
     while (e) {
         if (e & 1) r = r * x % q;
@@ -23,23 +29,23 @@ constexpr uint32_t c_powmod(uint32_t b, uint64_t e, uint32_t q) {
     }
     return (uint32_t)r;
 }
-constexpr uint32_t c_log2(uint32_t n) {
+QT_CHD uint32_t c_log2(uint32_t n) {
     uint32_t l = 0;
     while ((1u << l) < n) l++;
     return l;
 }
-constexpr uint32_t c_neg_qinv32(uint32_t q) {  // -q^-1 mod 2^32 (PARAM_QINV, main.cuh:15)
+QT_CHD uint32_t c_neg_qinv32(uint32_t q) {  // -q^-1 mod 2^32 (PARAM_QINV, main.cuh:15)
     uint32_t inv = q;
     for (int i = 0; i < 5; i++) inv *= 2u - q * inv;
     return 0u - inv;
 }
-constexpr uint32_t c_find_psi(uint32_t n, uint32_t q) {  // smallest g with g^((q-1)/2n) of order 2n
+QT_CHD uint32_t c_find_psi(uint32_t n, uint32_t q) {  // smallest g with g^((q-1)/2n) of order 2n
     for (uint32_t g = 2;; g++) {
         uint32_t psi = c_powmod(g, (q - 1) / (2 * n), q);
         if (c_powmod(psi, n, q) == q - 1) return psi;
     }
 }
-constexpr uint32_t c_bitrev(uint32_t x, uint32_t bits) {
+QT_CHD uint32_t c_bitrev(uint32_t x, uint32_t bits) {
     uint32_t r = 0;
     for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
     return r;
