@@ -56,6 +56,30 @@ template <int OP> __device__ __forceinline__ void step(uint32_t (&r)[CHAINS], ui
             w[i] = (uint64_t)__double_as_longlong(d);
             asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));
         }
+        if (OP == 14 || OP == 15 || OP == 16) {  // fp64 Shoup-style butterfly: 5 DP ops, exact for |y|<2^30
+            double yv = __longlong_as_double((long long)w[i]);   // operand y (also plays x)
+            const double W = 2083362.0, WQ = 2083362.0 / 8404993.0, Qd = 8404993.0;
+            const double MAGIC = 6755399441055744.0, QM = 8404993.0 * 6755399441055744.0;
+            double hm, u, t, xp, yp;
+            asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(hm) : "d"(yv), "d"(WQ), "d"(MAGIC));
+            asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(u) : "d"(-Qd), "d"(hm), "d"(QM));
+            asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(t) : "d"(yv), "d"(W), "d"(u));
+            asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(xp) : "d"(yv), "d"(t));
+            asm volatile("sub.rn.f64 %0, %1, %2;" : "=d"(yp) : "d"(xp), "d"(t));
+            w[i] = (uint64_t)__double_as_longlong(yp);
+        }
+        if (OP == 15 || OP == 16) {  // + integer Shoup butterflies in the same thread (other polynomial)
+            for (int rep = 0; rep < (OP == 16 ? 2 : 1); rep++) {
+                uint32_t hi, t;
+                asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(r[i]), "r"(c));
+                asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(r[i]), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(hi), "r"(0u - 8404993u));
+                uint32_t x = r[i] ^ 0x5555u;
+                asm volatile("add.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(x), "r"(t));
+                asm volatile("sub.u32 %0, %1, %2;" : "=r"(x) : "r"(r[i]), "r"(t));
+                r[i] ^= x;
+            }
+        }
         if (OP == 13) {  // mul.hi + fp32 fma interleaved: does FFMA find room beside IMAD.HI?
             asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
             float f = __uint_as_float((uint32_t)w[i]);
@@ -124,6 +148,9 @@ int main() {
     run<11>("fma_f32", 1, p.multiProcessorCount, out, cyc, false);
     run<12>("fma_f64_plus_mad_lo (2 instr)", 2, p.multiProcessorCount, out, cyc, false);
     run<13>("mul_hi_plus_fma_f32 (2 instr)", 2, p.multiProcessorCount, out, cyc, false);
+    run<14>("fp64_butterfly (5 instr = 1 butterfly)", 5, p.multiProcessorCount, out, cyc, false);
+    run<15>("fp64_butterfly + int_butterfly (10 instr = 2 butterflies)", 10, p.multiProcessorCount, out, cyc, false);
+    run<16>("fp64_butterfly + 2 int_butterflies (15 instr = 3 butterflies)", 15, p.multiProcessorCount, out, cyc, false);
     run<8>("mad_lo_plus_add (2 instr)", 2, p.multiProcessorCount, out, cyc, false);
     run<7>("shoup_butterfly (5 instr, 3 mul)", 5, p.multiProcessorCount, out, cyc, true);
     printf("}\n");
