@@ -110,6 +110,13 @@ int qt_pointwise(qt_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint32_t
  * per operand.  Replaces the 31-34 launches of test_NTT_{Stockham,GS_CT,CT_CT,GS_GS,CT_GS}_nega_gpu
  * (NTT.cu:2008-2443, between the memcpys).  d_z may alias d_x or d_y. */
 int qt_polymul(qt_ctx* ctx, const uint32_t* d_x, const uint32_t* d_y, uint32_t* d_z, size_t batch);
+/* z[b] = a[b]*y[b] with NTT(a) supplied: d_a_hat is what qt_ntt_forward left (canonical, bit-reversed
+ * order).  broadcast != 0: ONE polynomial a_hat (n words) multiplies every y[b] — qTESLA's own shape
+ * (public a, many secrets/challenges; the caller of the reference's path pays the transform of a once
+ * instead of per product).  broadcast == 0: one a_hat per product (batch*n words).  Operands must be
+ * 16-byte aligned.  d_z may alias d_y. */
+int qt_polymul_ntt(qt_ctx* ctx, const uint32_t* d_a_hat, int broadcast, const uint32_t* d_y, uint32_t* d_z,
+                   size_t batch);
 /* reorder between the two NTT-domain orderings; replaces bit_reverse_copy_tbl_gpu (NTT.cu:487-492).
  * d_out must not alias d_in. */
 int qt_bitrev_copy(qt_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, size_t batch);

@@ -93,6 +93,9 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
         (void)cudaGetLastError();
     }
     c->grid_tma = c->occ_tma * c->num_sms;
+    (void)cudaFuncSetAttribute(k_polymul_ntt<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
+    (void)cudaFuncSetAttribute(k_polymul_ntt<SET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
+    (void)cudaGetLastError();
     QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_forward<SET>, WARPS_PER_CTA * 32, S::SMEM_DIRECT));
     c->grid_fwd = std::max(1, occ) * c->num_sms;
     QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_inverse<SET>, WARPS_PER_CTA * 32, S::SMEM_DIRECT));
@@ -144,6 +147,16 @@ template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32
     else
         k_polymul<SET><<<grid_for(c->grid_fused, tiles), WARPS_PER_CTA * 32, c->smem_fused, s>>>(
             x, y, z, B, c->d_lane_fwd);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool bcast, const uint32_t* y, uint32_t* z, size_t B) {
+    const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
+    if (c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
+    if ((((uintptr_t)ahat | (uintptr_t)y) & 15) != 0) return QT_ERR_BAD_ARG;  // 128-bit / bulk-copy alignment
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS));
+    if (bcast) k_polymul_ntt<SET, true><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_lane_fwd);
+    else k_polymul_ntt<SET, false><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_lane_fwd);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -358,6 +371,12 @@ int qt_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, siz
     if (!B) return 0;
     DeviceGuard g(c->device);
     return QT_DISPATCH(c, launch_polymul, c, x, y, z, B, c->stream);
+}
+int qt_polymul_ntt(qt_ctx* c, const uint32_t* ahat, int broadcast, const uint32_t* y, uint32_t* z, size_t B) {
+    if (!c || ((!ahat || !y || !z) && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_polymul_ntt, c, ahat, broadcast != 0, y, z, B);
 }
 int qt_bitrev_copy(qt_ctx* c, const uint32_t* in, uint32_t* out, size_t B) {
     if (!c || ((!in || !out) && B) || (in == out && B)) return QT_ERR_BAD_ARG;

@@ -228,6 +228,88 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
     }
 }
 
+// z = a*y with NTT(a) supplied by the caller (qTESLA's own use: one public polynomial a, transformed
+// once, multiplied by many secrets / sparse challenges).  Two transforms instead of three.
+// a_hat is in the NTT domain exactly as qt_ntt_forward leaves it (canonical, bit-reversed order);
+// BCAST: one a_hat for the whole batch, otherwise one per product.  y is staged by TMA like above.
+template <int SET, bool BCAST>
+__global__ void __launch_bounds__(TmaCfg<SET>::WARPS * 32, 1)
+k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z, size_t batch,
+              const TwQuad* __restrict__ g_lane) {
+    using T = Tile<SET>;
+    using S = KernelShape<SET>;
+    using G = StageShape<SET>;
+    extern __shared__ uint4 smem_raw[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
+    constexpr int NW = TmaCfg<SET>::WARPS;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* B = s_stage + warp * 2 * G::WORDS;
+    uint64_t* bar_b = s_bar + 2 * warp;
+    const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+    const size_t stride = (size_t)gridDim.x * NW;
+    size_t tile = (size_t)blockIdx.x * NW + warp;
+    auto issue = [&](size_t t) {
+        const size_t p0 = t * T::PPW;
+        const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);
+        mbar_expect_tx(bar_b, np * T::N * (uint32_t)sizeof(uint32_t));
+        if (G::PAD == 0) {
+            bulk_g2s(B, y + p0 * T::N, np * T::N * (uint32_t)sizeof(uint32_t), bar_b);
+        } else {
+            for (uint32_t p = 0; p < np; p++)
+                bulk_g2s(B + p * G::POLY_STRIDE, y + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar_b);
+        }
+    };
+    if (lane == 0) {
+        mbar_init(bar_b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        if (tile < ntiles) issue(tile);
+    }
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    __syncthreads();
+    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
+    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    uint32_t phase = 0;
+    for (; tile < ntiles; tile += stride, phase ^= 1) {
+        const size_t base = tile * T::C::TILE_WORDS;
+        const bool valid = tile * T::PPW + lane / T::LPP < batch;
+        const bool more = tile + stride < ntiles;
+        // this lane's E words of a_hat in the cols layout (clamped for the missing polynomial of a tail tile)
+        const uint4* ah = reinterpret_cast<const uint4*>(
+            a_hat + (BCAST ? (size_t)T::E * (lane % T::BLOCKS) : (valid ? base + (size_t)T::E * lane : 0)));
+        uint32_t v[T::E];
+        mbar_wait(bar_b, phase);
+#pragma unroll
+        for (uint32_t r = 0; r < T::E; r++) v[r] = B[G::off(lane, r)];
+        __syncwarp();
+        T::fwd_rows(v);
+        T::sts_rows(v, B, lane);
+        __syncwarp();
+        T::lds_cols(v, B, lane);
+        T::fwd_cols(v, tw_f);
+#pragma unroll
+        for (uint32_t c = 0; c < T::E / 4; c++) {
+            const uint4 u = __ldg(ah + c);
+            const uint32_t b[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+                v[4 * c + k] = T::LAZY ? T::mul_mont(v[4 * c + k], b[k]) : T::mul_mont(T::csub(v[4 * c + k], T::TWO_Q), b[k]);
+        }
+        T::inv_cols(v, tw_i);
+        __syncwarp();
+        T::sts_cols(v, B, lane);
+        __syncwarp();
+        T::lds_rows(v, B, lane);
+        fence_proxy_async();
+        __syncwarp();
+        if (more && lane == 0) issue(tile + stride);
+        T::template inv_rows<UNI_INV_FUSED>(v);
+        T::store_rows(v, z + base, lane, valid);
+    }
+}
+
 // forward NTT in place: natural -> NTT domain (bit-reversed, psi merged), canonical
 template <int SET>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "qt_pointwise": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
     "qt_polymul": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
     "qt_bitrev_copy": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "qt_polymul_ntt": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _sz]),
     "qt_nussbaumer": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.c_int]),
     "qt_fill_uniform": (C.c_int, [_vp, _vp, _sz, C.c_uint64, C.c_uint64]),
     "qt_polymul_host": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
@@ -192,6 +193,11 @@ class Engine:
 
     def polymul(self, d_x, d_y, d_z, batch=None):
         _check(lib().qt_polymul(self._h, _addr(d_x), _addr(d_y), _addr(d_z), self._batch(d_x, batch)))
+
+    def polymul_ntt(self, d_a_hat, d_y, d_z, broadcast=True, batch=None):
+        """z = a*y with NTT(a) given (broadcast: one a_hat for the whole batch)"""
+        _check(lib().qt_polymul_ntt(self._h, _addr(d_a_hat), 1 if broadcast else 0, _addr(d_y), _addr(d_z),
+                                    self._batch(d_y, batch)))
 
     def bitrev_copy(self, d_in, d_out, batch=None):
         _check(lib().qt_bitrev_copy(self._h, _addr(d_in), _addr(d_out), self._batch(d_in, batch)))

@@ -275,3 +275,34 @@ def test_cxx_harness_reference_command_line():
     assert out.returncode == 0 and "4294966273 4294966275 4294966277" in out.stdout   # Nussbaumer ring KAT
     out = subprocess.run([exe, "-speedgpu", "3", "-set", "p-III", "-batch", "3"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and str((2 - 2048) % 856145921) in out.stdout
+
+
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_cached_transform_product(engines, oracle, s):
+    """qTESLA-shaped caller: one public polynomial a (transformed once) times many y, incl. sparse ternary y."""
+    import torch
+    eng = engines[s]
+    n, q = eng.n, eng.q
+    B = 41
+    rng = np.random.default_rng(70 + s)
+    a = rng.integers(0, q, n, dtype=np.uint32)
+    y = rng.integers(0, q, B * n, dtype=np.uint32)
+    for b in range(0, B, 3):                                   # every third y: weight-48 ternary challenge
+        row = np.zeros(n, np.uint32)
+        row[rng.choice(n, 48, replace=False)] = np.where(rng.random(48) < 0.5, 1, q - 1)
+        y[b * n:(b + 1) * n] = row
+    ta = torch.from_numpy(a.view(np.int32)).cuda()
+    eng.ntt_forward(ta)                                        # NTT(a), once
+    ty = torch.from_numpy(y.view(np.int32)).cuda()
+    tz = torch.empty_like(ty)
+    eng.polymul_ntt(ta, ty, tz, broadcast=True)
+    eng.synchronize()
+    ref = oracle.polymul(s, np.tile(a, B), y)
+    assert np.array_equal(tz.cpu().numpy().view(np.uint32), ref)
+    # per-product a_hat
+    aa = rng.integers(0, q, B * n, dtype=np.uint32)
+    taa = torch.from_numpy(aa.view(np.int32)).cuda()
+    eng.ntt_forward(taa)
+    eng.polymul_ntt(taa, ty, tz, broadcast=False)
+    eng.synchronize()
+    assert np.array_equal(tz.cpu().numpy().view(np.uint32), oracle.polymul(s, aa, y))

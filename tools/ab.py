@@ -41,6 +41,14 @@ for name in args.sets.split(","):
             print(f"{name:6s} variant {v}: {r/1e6:8.2f} M polymul/s  info={eng.kernel_info()}", flush=True)
         except Exception as ex:
             print(f"{name:6s} variant {v}: {ex}")
+    try:
+        ah = torch.empty(eng.n, dtype=torch.int32, device="cuda")
+        with torch.cuda.stream(stream):
+            eng.fill_uniform(ah, 3, 0); eng.ntt_forward(ah)
+        r = timeit(lambda: eng.polymul_ntt(ah, y, z, True, B), args.steps)
+        print(f"{name:6s} cached a_hat (broadcast): {r/1e6:8.2f} M polymul/s", flush=True)
+    except Exception as ex:
+        print(f"{name:6s} cached: {ex}")
     if args.nuss:
         for ring in (0, 1):
             try:
