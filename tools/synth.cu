@@ -1,0 +1,66 @@
+// synth.cu — how fast does the compiler-generated butterfly code of qt_tile.cuh run when nothing else
+// is in the way?  Register-only loops over Tile<SET_III>::fwd_rows / inv_rows (uniform twiddles) and
+// fwd_cols / inv_cols (twiddles from shared memory), 16 warps per SM like the fused kernel.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/synth tools/synth.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <vector>
+#include "../ntt-gpu-qtesla_b200/csrc/qt_tile.cuh"
+namespace qt { TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX]; }
+using namespace qt;
+using T = Tile<SET_III>;
+
+template <int MODE> __global__ void __launch_bounds__(512, 1) k(uint32_t* out, const TwQuad* g_tw, int iters, long long* cyc) {
+    extern __shared__ uint4 sm[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(sm);
+    for (int i = threadIdx.x; i < (int)(T::SLOT_PAIRS * T::BLOCKS); i += blockDim.x) s_tw[i] = g_tw[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t v[T::E];
+    for (uint32_t r = 0; r < T::E; r++) v[r] = threadIdx.x * 33 + r;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        if (MODE == 0) T::fwd_rows(v);
+        if (MODE == 1) T::fwd_cols(v, s_tw + lane);
+        if (MODE == 2) { T::fwd_rows(v); T::fwd_cols(v, s_tw + lane); }
+        if (MODE == 3) { T::inv_cols(v, s_tw + 31 - lane); T::inv_rows<UNI_INV_FUSED>(v); }
+        if (MODE == 4) { T::fwd_rows(v); T::fwd_cols(v, s_tw + lane); T::inv_cols(v, s_tw + 31 - lane); T::inv_rows<UNI_INV_FUSED>(v); }
+    }
+    long long t1 = clock64();
+    uint32_t s = 0;
+    for (uint32_t r = 0; r < T::E; r++) s += v[r];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE> void run(const char* name, double bf_per_iter, int sms, uint32_t* out, const TwQuad* tw, long long* cyc) {
+    const int iters = 400, smem = T::SLOT_PAIRS * T::BLOCKS * sizeof(TwQuad);
+    k<MODE><<<sms, 512, smem>>>(out, tw, 10, cyc);
+    cudaDeviceSynchronize();
+    k<MODE><<<sms, 512, smem>>>(out, tw, iters, cyc);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(sms);
+    cudaMemcpy(h.data(), cyc, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (auto c : h) mx = c > mx ? c : mx;
+    // per SMSP: 4 warps, each does bf_per_iter warp-butterflies per iteration
+    const double clk_per_warp_bf = (double)mx / (iters * bf_per_iter * 4.0);
+    printf("  \"%s\": {\"clk_per_warp_butterfly_per_smsp\": %.3f, \"fraction_of_8clk_model\": %.3f},\n", name, clk_per_warp_bf, 8.0 / clk_per_warp_bf);
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    HostTables tab; build_tables(SET_III, &tab);
+    cudaMemcpyToSymbol(c_uni, tab.uni, sizeof(tab.uni), (size_t)SET_III * sizeof(tab.uni));
+    TwQuad* tw; cudaMalloc(&tw, tab.lane_fwd.size() * sizeof(TwQuad));
+    cudaMemcpy(tw, tab.lane_fwd.data(), tab.lane_fwd.size() * sizeof(TwQuad), cudaMemcpyHostToDevice);
+    uint32_t* out; long long* cyc;
+    cudaMalloc(&out, (size_t)p.multiProcessorCount * 512 * 4); cudaMalloc(&cyc, p.multiProcessorCount * 8);
+    printf("{\n");
+    run<0>("fwd_rows (80 butterflies, uniform twiddles)", 80, p.multiProcessorCount, out, tw, cyc);
+    run<1>("fwd_cols (80 butterflies, smem twiddles)", 80, p.multiProcessorCount, out, tw, cyc);
+    run<2>("forward transform (160)", 160, p.multiProcessorCount, out, tw, cyc);
+    run<3>("inverse transform (160 + 16 + folds)", 160, p.multiProcessorCount, out, tw, cyc);
+    run<4>("forward + inverse (320)", 320, p.multiProcessorCount, out, tw, cyc);
+    printf("  \"note\": \"16 warps per SM, registers only\"\n}\n");
+    return 0;
+}
