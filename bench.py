@@ -166,7 +166,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(set_id, p, batch, gpus):
@@ -221,7 +221,27 @@ def cpu_baseline(set_id, o):
     }
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries write to fd 1 (NCCL's version banner, the reference's `count:` prints) goes to
+    stderr; the ONE JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -424,7 +444,7 @@ def main():
             line["other_configs"] = extras
             line["fused_variants"] = variants
             line["nussbaumer"] = nuss
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
