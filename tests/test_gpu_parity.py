@@ -306,3 +306,44 @@ def test_cached_transform_product(engines, oracle, s):
     eng.polymul_ntt(taa, ty, tz, broadcast=False)
     eng.synchronize()
     assert np.array_equal(tz.cpu().numpy().view(np.uint32), oracle.polymul(s, aa, y))
+
+
+def test_unaligned_operands_take_the_direct_kernel(engines, oracle):
+    """TMA bulk copies need 16-byte alignment; 4-byte aligned views must still work (direct-load kernel)."""
+    import torch
+    eng = engines[1]
+    B = 19
+    x, y = rand_pair(eng.q, B * eng.n, 31337)
+    tx = torch.zeros(B * eng.n + 1, dtype=torch.int32, device="cuda")
+    ty = torch.zeros(B * eng.n + 3, dtype=torch.int32, device="cuda")
+    tz = torch.zeros(B * eng.n + 1, dtype=torch.int32, device="cuda")
+    tx[1:].copy_(torch.from_numpy(x.view(np.int32)))
+    ty[3:].copy_(torch.from_numpy(y.view(np.int32)))
+    eng.polymul(tx.data_ptr() + 4, ty.data_ptr() + 12, tz.data_ptr() + 4, B)
+    eng.synchronize()
+    assert np.array_equal(tz[1:].cpu().numpy().view(np.uint32), oracle.polymul(1, x, y))
+    assert int(tz[0]) == 0
+
+
+def test_batch_beyond_32bit_word_index(engines, oracle):
+    """4 Mi + 5 polynomials of n=1024: more than 2^32 coefficients per array (16 GiB each) — 64-bit indexing in
+    the kernels, the generator and the TMA addresses.  Checked on the first and last polynomials."""
+    import torch
+    eng = engines[1]
+    n = eng.n
+    B = (1 << 22) + 5
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 * B * n * 4 + (2 << 30):
+        pytest.skip("not enough device memory")
+    x = torch.empty(B * n, dtype=torch.int32, device="cuda")
+    y = torch.empty_like(x); z = torch.empty_like(x)
+    eng.fill_uniform(x, 1, 0); eng.fill_uniform(y, 2, 0)
+    eng.polymul(x, y, z)
+    eng.synchronize()
+    for lo in (0, (1 << 22) - 2, B - 3):
+        xs = x[lo * n:(lo + 3) * n].cpu().numpy().view(np.uint32)
+        ys = y[lo * n:(lo + 3) * n].cpu().numpy().view(np.uint32)
+        assert np.array_equal(xs, oracle.splitmix(1, lo * n, eng.q, 3 * n))
+        assert np.array_equal(z[lo * n:(lo + 3) * n].cpu().numpy().view(np.uint32), oracle.polymul(1, xs, ys))
+    del x, y, z
+    torch.cuda.empty_cache()
