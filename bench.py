@@ -428,7 +428,9 @@ def main():
                          "peak_source": peaks_src, "kernel": "k_polymul_tma" if eng.kernel_info()["block"] != 256 else "k_polymul",
                          "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_pp * batch,
-                         "note": "HBM view; the binding roofline is the integer-multiply pipe, see roofline_int"},
+                         "binding": "int_mul_pipe", "binding_frac": int_achieved / int_peak,
+                         "note": "HBM view (this contract key); the BINDING roofline is the integer-multiply pipe: "
+                                 "roofline_int, confirmed by ncu sm__pipe_fmaheavy_cycles_active (profiles/)"},
             "roofline_int": {"bound": "int_mul_pipe", "achieved": int_achieved / 1e12, "peak": int_peak / 1e12,
                              "unit": "T mul-pipe slots/s (mul.lo = 1 slot, mul.hi/wide = 2)", "frac": int_achieved / int_peak,
                              "peak_source": int_src, "algorithmic_slots_per_polymul": slots_pp,

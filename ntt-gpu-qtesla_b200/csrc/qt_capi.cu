@@ -93,6 +93,9 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
         (void)cudaGetLastError();
     }
     c->grid_tma = c->occ_tma * c->num_sms;
+    (void)cudaFuncSetAttribute(k_ntt_tma<SET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
+    (void)cudaFuncSetAttribute(k_ntt_tma<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
+    (void)cudaFuncSetAttribute(k_bitrev_copy<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BitrevShape<SET>::SMEM);
     (void)cudaFuncSetAttribute(k_polymul_ntt<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
     (void)cudaFuncSetAttribute(k_polymul_ntt<SET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
     (void)cudaGetLastError();
@@ -160,13 +163,22 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
     c->launches++;
     return (int)cudaGetLastError();
 }
+template <int SET, bool INV> int launch_ntt_tma(qt_ctx* c, uint32_t* a, size_t B) {
+    const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS));
+    k_ntt_tma<SET, INV><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(a, B, c->d_lane_fwd);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
 template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
+    if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, false>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     k_ntt_forward<SET><<<grid_for(c->grid_fwd, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_fwd);
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <int SET> int launch_inverse(qt_ctx* c, uint32_t* a, size_t B) {
+    if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, true>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_fwd);
     c->launches++;
@@ -180,9 +192,9 @@ template <int SET> int launch_pointwise(qt_ctx* c, const uint32_t* a, const uint
     return (int)cudaGetLastError();
 }
 template <int SET> int launch_bitrev(qt_ctx* c, const uint32_t* in, uint32_t* out, size_t B) {
-    const size_t words = B * Cfg<SET>::N;
-    const int grid = (int)std::min<size_t>((size_t)c->num_sms * 8, (words + 255) / 256);
-    k_bitrev_copy<SET><<<std::max(1, grid), 256, 0, c->stream>>>(in, out, words);
+    using S = BitrevShape<SET>;
+    const int grid = (int)std::min<size_t>((size_t)c->num_sms * 6, (B + S::WARPS - 1) / S::WARPS);
+    k_bitrev_copy<SET><<<std::max(1, grid), S::WARPS * 32, S::SMEM, c->stream>>>(in, out, B);
     c->launches++;
     return (int)cudaGetLastError();
 }

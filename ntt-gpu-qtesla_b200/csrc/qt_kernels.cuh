@@ -381,6 +381,88 @@ k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     }
 }
 
+// TMA-staged single transform (forward or inverse), in place.  Two one-tile buffers per warp alternate
+// between "staging of the next tile" (bulk copy in flight) and "current tile: staging, then transposition
+// scratch".  Same arithmetic as k_ntt_forward / k_ntt_inverse, which remain the fallback for operands
+// that are not 16-byte aligned.
+template <int SET, bool INVERSE>
+__global__ void __launch_bounds__(TmaCfg<SET>::WARPS * 32, 1)
+k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
+    using T = Tile<SET>;
+    using S = KernelShape<SET>;
+    using G = StageShape<SET>;
+    extern __shared__ uint4 smem_raw[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
+    constexpr int NW = TmaCfg<SET>::WARPS;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* buf0 = s_stage + warp * 2 * G::WORDS;
+    uint64_t* bar0 = s_bar + 2 * warp;
+    const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+    const size_t stride = (size_t)gridDim.x * NW;
+    size_t tile = (size_t)blockIdx.x * NW + warp;
+    auto issue = [&](uint32_t* st, uint64_t* bar, size_t t) {
+        const size_t p0 = t * T::PPW;
+        const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);
+        mbar_expect_tx(bar, np * T::N * (uint32_t)sizeof(uint32_t));
+        if (G::PAD == 0) {
+            bulk_g2s(st, a + p0 * T::N, np * T::N * (uint32_t)sizeof(uint32_t), bar);
+        } else {
+            for (uint32_t p = 0; p < np; p++)
+                bulk_g2s(st + p * G::POLY_STRIDE, a + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar);
+        }
+    };
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        if (tile < ntiles) issue(buf0, bar0, tile);
+    }
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    __syncthreads();
+    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
+    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    for (uint32_t k = 0; tile < ntiles; tile += stride, k++) {
+        uint32_t* cur = buf0 + (k & 1) * G::WORDS;
+        uint32_t* nxt = buf0 + ((k & 1) ^ 1) * G::WORDS;
+        const size_t base = tile * T::C::TILE_WORDS;
+        const bool valid = tile * T::PPW + lane / T::LPP < batch;
+        // the other buffer was last read (as scratch) in the previous iteration, which ended with a __syncwarp
+        if (tile + stride < ntiles && lane == 0) {
+            fence_proxy_async();
+            issue(nxt, bar0 + ((k & 1) ^ 1), tile + stride);
+        }
+        mbar_wait(bar0 + (k & 1), (k >> 1) & 1);
+        uint32_t v[T::E];
+#pragma unroll
+        for (uint32_t r = 0; r < T::E; r++) v[r] = cur[G::off(lane, r)];
+        __syncwarp();
+        if (!INVERSE) {
+            T::fwd_rows(v);
+            T::sts_rows(v, cur, lane);
+            __syncwarp();
+            T::lds_cols(v, cur, lane);
+            T::fwd_cols(v, tw_f);
+            T::canon_fwd(v);
+        } else {
+            T::sts_rows(v, cur, lane);  // re-layout: NTT-domain data is consumed in the cols layout
+            __syncwarp();
+            T::lds_cols(v, cur, lane);
+            T::inv_cols(v, tw_i);
+        }
+        __syncwarp();
+        T::sts_cols(v, cur, lane);
+        __syncwarp();
+        T::lds_rows(v, cur, lane);
+        fence_proxy_async();
+        __syncwarp();
+        if (INVERSE) T::template inv_rows<UNI_INV_PLAIN>(v);
+        T::store_rows(v, a + base, lane, valid);
+    }
+}
+
 // c = a*b mod q element-wise (HBM-bound: 12 bytes per coefficient)
 template <int SET>
 __global__ void __launch_bounds__(256)
@@ -403,15 +485,43 @@ k_pointwise(const uint32_t* a, const uint32_t* b, uint32_t* c, size_t words) {
 }
 
 // out[b*n + j] = in[b*n + brv(j)]   (bit_reverse_copy_tbl_gpu, NTT.cu:487-492)
+// One warp per polynomial.  Lane L reads the coefficients L + 32 r (one 128-byte line per warp
+// instruction); their bit-reversed positions brv(L + 32 r) = R*brv5(L) + brv_logR(r), R = n/32, form ONE
+// contiguous run of R words, so the permutation inside the run is a compile-time register renaming.  The
+// runs are turned back into coalesced rows through a padded shared-memory tile (row stride R+1), so both
+// the global read and the global write are full lines — no scattered gather (the reference's
+// table-driven gather uses 4 bytes of every 32-byte sector it touches).
+template <int SET> struct BitrevShape {
+    static constexpr uint32_t R = Cfg<SET>::N / 32, LOGR = Cfg<SET>::LOGN - 5, WARPS = 8;
+    static constexpr uint32_t WARP_WORDS = 32 * (R + 1);
+    static constexpr size_t SMEM = (size_t)WARPS * WARP_WORDS * sizeof(uint32_t);
+};
 template <int SET>
 __global__ void __launch_bounds__(256)
-k_bitrev_copy(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t words) {
+k_bitrev_copy(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch) {
     using C = Cfg<SET>;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t j = (uint32_t)(i & (C::N - 1));
-        const uint32_t rj = __brev(j) >> (32 - C::LOGN);
-        out[i] = in[i - j + rj];
+    using S = BitrevShape<SET>;
+    constexpr uint32_t R = S::R, LOGR = S::LOGR;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw) + warp * S::WARP_WORDS;
+    const uint32_t rl = __brev(lane) >> 27;  // brv5(lane): the output run this lane's inputs belong to
+    const size_t warps = (size_t)gridDim.x * S::WARPS;
+    for (size_t p = (size_t)blockIdx.x * S::WARPS + warp; p < batch; p += warps) {
+        const uint32_t* src = in + p * C::N + lane;
+        uint32_t v[R];
+#pragma unroll
+        for (uint32_t r = 0; r < R; r++) v[r] = src[32 * r];
+#pragma unroll
+        for (uint32_t k = 0; k < R; k++) buf[rl * (R + 1) + k] = v[c_bitrev(k, LOGR)];  // out[rl*R + k]
+        __syncwarp();
+        uint32_t* dst = out + p * C::N + lane;
+#pragma unroll
+        for (uint32_t r = 0; r < R; r++) {
+            const uint32_t o = lane + 32 * r;                                            // coalesced output index
+            dst[32 * r] = buf[(o / R) * (R + 1) + (o % R)];
+        }
+        __syncwarp();
     }
 }
 
