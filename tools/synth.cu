@@ -10,7 +10,7 @@ namespace qt { TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX]; }
 using namespace qt;
 using T = Tile<SET_III>;
 
-template <int MODE> __global__ void __launch_bounds__(512, 1) k(uint32_t* out, const TwQuad* g_tw, int iters, long long* cyc) {
+template <int MODE> __global__ void __launch_bounds__(768, 1) k(uint32_t* out, const TwQuad* g_tw, int iters, long long* cyc) {
     extern __shared__ uint4 sm[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(sm);
     for (int i = threadIdx.x; i < (int)(T::SLOT_PAIRS * T::BLOCKS); i += blockDim.x) s_tw[i] = g_tw[i];
@@ -33,17 +33,18 @@ template <int MODE> __global__ void __launch_bounds__(512, 1) k(uint32_t* out, c
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+static int g_threads = 512;
 template <int MODE> void run(const char* name, double bf_per_iter, int sms, uint32_t* out, const TwQuad* tw, long long* cyc) {
     const int iters = 400, smem = T::SLOT_PAIRS * T::BLOCKS * sizeof(TwQuad);
-    k<MODE><<<sms, 512, smem>>>(out, tw, 10, cyc);
+    k<MODE><<<sms, g_threads, smem>>>(out, tw, 10, cyc);
     cudaDeviceSynchronize();
-    k<MODE><<<sms, 512, smem>>>(out, tw, iters, cyc);
+    k<MODE><<<sms, g_threads, smem>>>(out, tw, iters, cyc);
     cudaDeviceSynchronize();
     std::vector<long long> h(sms);
     cudaMemcpy(h.data(), cyc, sms * sizeof(long long), cudaMemcpyDeviceToHost);
     long long mx = 0; for (auto c : h) mx = c > mx ? c : mx;
     // per SMSP: 4 warps, each does bf_per_iter warp-butterflies per iteration
-    const double clk_per_warp_bf = (double)mx / (iters * bf_per_iter * 4.0);
+    const double clk_per_warp_bf = (double)mx / (iters * bf_per_iter * (g_threads / 128.0));
     printf("  \"%s\": {\"clk_per_warp_butterfly_per_smsp\": %.3f, \"fraction_of_8clk_model\": %.3f},\n", name, clk_per_warp_bf, 8.0 / clk_per_warp_bf);
 }
 
@@ -54,8 +55,15 @@ int main() {
     TwQuad* tw; cudaMalloc(&tw, tab.lane_fwd.size() * sizeof(TwQuad));
     cudaMemcpy(tw, tab.lane_fwd.data(), tab.lane_fwd.size() * sizeof(TwQuad), cudaMemcpyHostToDevice);
     uint32_t* out; long long* cyc;
-    cudaMalloc(&out, (size_t)p.multiProcessorCount * 512 * 4); cudaMalloc(&cyc, p.multiProcessorCount * 8);
+    cudaMalloc(&out, (size_t)p.multiProcessorCount * 768 * 4); cudaMalloc(&cyc, p.multiProcessorCount * 8);
     printf("{\n");
+    for (int th : {128, 256, 384, 768}) {  // how many warps in butterfly code does the pipe need?
+        g_threads = th;
+        char nm[64];
+        snprintf(nm, sizeof nm, "forward transform (160), %d warps per SM", th / 32);
+        run<2>(nm, 160, p.multiProcessorCount, out, tw, cyc);
+    }
+    g_threads = 512;
     run<0>("fwd_rows (80 butterflies, uniform twiddles)", 80, p.multiProcessorCount, out, tw, cyc);
     run<1>("fwd_cols (80 butterflies, smem twiddles)", 80, p.multiProcessorCount, out, tw, cyc);
     run<2>("forward transform (160)", 160, p.multiProcessorCount, out, tw, cyc);
