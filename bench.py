@@ -409,6 +409,36 @@ def main():
                 e2.close()
             except Exception as ex:
                 nuss[rname] = str(ex)
+        # the unfused entry points, same batch, device-resident
+        unfused = {}
+        e2 = qt.Engine(set_id, local_rank)
+        e2.set_stream(stream.cuda_stream)
+        w = torch.empty_like(x)
+
+        def timed(fn, reps=20):
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    fn()
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(reps):
+                    fn()
+                a1.record(stream)
+            a1.synchronize()
+            return a0.elapsed_time(a1) / reps
+        w.copy_(x)
+        for nm, fn, bytes_per_coeff in (("qt_ntt_forward", lambda: e2.ntt_forward(w, batch), 8), ("qt_ntt_inverse", lambda: e2.ntt_inverse(w, batch), 8),
+                                        ("qt_pointwise", lambda: e2.pointwise(x, y, w, batch), 12), ("qt_bitrev_copy", lambda: e2.bitrev_copy(x, w, batch), 8)):
+            t = timed(fn)
+            unfused[nm] = {"polys_per_s": batch / (t * 1e-3), "GB_per_s": batch * p.n * bytes_per_coeff / (t * 1e-3) / 1e9,
+                           "hbm_frac": batch * p.n * bytes_per_coeff / (t * 1e-3) / 1e9 / float(peaks["hbm_gbs"])}
+        ah = torch.empty(p.n, dtype=torch.int32, device=dev)
+        with torch.cuda.stream(stream):
+            e2.fill_uniform(ah, 3, 0); e2.ntt_forward(ah, 1)
+        t = timed(lambda: e2.polymul_ntt(ah, y, w, True, batch))
+        unfused["qt_polymul_ntt (cached NTT(a), broadcast)"] = {"polymuls_per_s": batch / (t * 1e-3)}
+        del w
+        e2.close()
         from oracle_lib import Oracle
         cpu = cpu_baseline(set_id, Oracle())
 
@@ -446,6 +476,7 @@ def main():
             line["other_configs"] = extras
             line["fused_variants"] = variants
             line["nussbaumer"] = nuss
+            line["unfused_entry_points"] = unfused
         emit(line)
     eng.close()
     if world > 1:
