@@ -346,16 +346,17 @@ def main():
         except Exception:
             traffic = None
 
-    # parity check of the timed buffers against the oracle: 1024 polynomials incl. first/last of the shard
-    parity = None
-    if rank == 0:
-        from oracle_lib import Oracle
-        o = Oracle()
-        half = min(512, batch // 2)
-        pick = lambda t: np.concatenate([t[: half * p.n].cpu().numpy(), t[(batch - half) * p.n:].cpu().numpy()]).view(np.uint32)
-        xs, ys, zs = pick(x), pick(y), pick(z)
-        gen_ok = bool(np.array_equal(xs[: p.n], o.splitmix(1, 0, p.q, p.n)))
-        parity = bool(np.array_equal(zs, o.polymul(set_id, xs, ys, threads=host_threads()))) and gen_ok
+    # parity check of the timed buffers against the oracle on EVERY rank: 1024 polynomials incl. the first
+    # and last of the rank's shard, and the shard's slice of the synthetic stream
+    from oracle_lib import Oracle
+    o = Oracle()
+    half = min(512, batch // 2)
+    pick = lambda t: np.concatenate([t[: half * p.n].cpu().numpy(), t[(batch - half) * p.n:].cpu().numpy()]).view(np.uint32)
+    xs, ys, zs = pick(x), pick(y), pick(z)
+    first = qt.sharding.weak_scaling_slice(batch, p.n, rank)
+    gen_ok = bool(np.array_equal(xs[: p.n], o.splitmix(1, first, p.q, p.n)))
+    par_ok = bool(np.array_equal(zs, o.polymul(set_id, xs, ys, threads=max(1, host_threads() // world)))) and gen_ok
+    parity = max_over_ranks(0.0 if par_ok else 1.0) == 0.0
 
     # end-to-end: host buffers through qt_polymul_host (H2D + kernel + D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, 10))
@@ -467,7 +468,8 @@ def main():
                              "algorithmic_mul_instr_per_polymul": imad_pp,
                              "frac_survey_definition": per_gpu_rate * imad_pp / int_peak,
                              "note": "binding roofline; compare with ncu sm__pipe_fmaheavy_cycles_active in profiles/"},
-            "parity_check": {"ok": parity, "polynomials": 2 * min(512, batch // 2), "against": "CPU oracle (oracle/qt_oracle.c)"},
+            "parity_check": {"ok": parity, "polynomials_per_rank": 2 * min(512, batch // 2), "ranks_checked": world,
+                             "against": "CPU oracle (oracle/qt_oracle.c)"},
             "kernel_info": eng.kernel_info(),
         }
         if cpu is not None:

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -210,6 +211,10 @@ int ensure_pipe(qt_ctx* c) {
     // chunk: 4096 polynomials of n=1024 (16 MiB per operand) — large enough for PCIe efficiency,
     // small enough that three slots overlap H2D, compute and D2H
     c->pipe_polys = (size_t)(4u << 20) / c->p.n;
+    if (const char* e = getenv("QT_PIPE_CHUNK_WORDS")) {  // tuning aid: coefficients per operand per chunk
+        const size_t w = strtoull(e, nullptr, 10);
+        if (w >= c->p.n) c->pipe_polys = w / c->p.n;
+    }
     for (int i = 0; i < qt_ctx::PIPE; i++) {
         QT_CUDA(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));
         QT_CUDA(cudaMalloc(&c->pipe_buf[i], 2 * c->pipe_polys * c->p.n * sizeof(uint32_t)));
