@@ -138,6 +138,8 @@ int qt_polymul_host(qt_ctx* ctx, const uint32_t* x, const uint32_t* y, uint32_t*
  * one host thread + stream per device, no collective. */
 int qt_polymul_host_multi(int param_set, const uint32_t* x, const uint32_t* y, uint32_t* z,
                           size_t batch, int ngpus);
+/* releases the per-device contexts qt_polymul_host_multi keeps between calls */
+int qt_shutdown(void);
 int qt_nussbaumer_host(qt_ctx* ctx, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
                        int ring);
 

@@ -5,10 +5,11 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB = os.path.join(PKG_DIR, "libqtesla_b200.so")
-SOURCES = [os.path.join(CSRC, "qt_capi.cu")]
+SOURCES = [os.path.join(CSRC, "qt_capi.cu"), os.path.join(CSRC, "qt_reference_api.cpp")]
 HEADERS = [os.path.join(CSRC, f) for f in
            ("qt_params.h", "qt_tables.h", "qt_tile.cuh", "qt_kernels.cuh", "qt_nussbaumer.cuh")] + [
-    os.path.join(os.path.dirname(PKG_DIR), "include", "qtesla_b200.h")]
+    os.path.join(os.path.dirname(PKG_DIR), "include", "qtesla_b200.h"),
+    os.path.join(os.path.dirname(PKG_DIR), "include", "qtesla_b200_reference_api.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

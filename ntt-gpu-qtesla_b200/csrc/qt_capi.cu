@@ -458,14 +458,20 @@ int qt_nussbaumer_host(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t
     return host_pipeline(c, x, y, z, B, ring);
 }
 
+// contexts of the one-shot multi-GPU form are created once per (set, device) and reused
+static std::mutex g_multi_mutex;
+static qt_ctx* g_multi_ctx[NUM_SETS][64];
+
 int qt_polymul_host_multi(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ngpus) {
     RtParams p;
     if (!rt_params(set, &p)) return QT_ERR_BAD_SET;
     if ((!x || !y || !z) && B) return QT_ERR_BAD_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return QT_ERR_NO_DEVICE;
+    ndev = std::min(ndev, 64);
     if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
     if (!B) return 0;
+    std::lock_guard<std::mutex> lk(g_multi_mutex);  // contexts are not thread-safe
     // contiguous slices [g*B/G, (g+1)*B/G), one host thread per device, no collective
     std::vector<int> rcs(ngpus, 0);
     std::vector<std::thread> th;
@@ -473,16 +479,23 @@ int qt_polymul_host_multi(int set, const uint32_t* x, const uint32_t* y, uint32_
         th.emplace_back([&, gidx]() {
             const size_t lo = B * gidx / ngpus, hi = B * (gidx + 1) / ngpus;
             if (hi == lo) return;
-            qt_ctx* c = nullptr;
-            int rc = qt_create(set, gidx, &c);
-            if (!rc) rc = qt_polymul_host(c, x + lo * p.n, y + lo * p.n, z + lo * p.n, hi - lo);
-            qt_destroy(c);
+            int rc = 0;
+            if (!g_multi_ctx[set][gidx]) rc = qt_create(set, gidx, &g_multi_ctx[set][gidx]);
+            if (!rc) rc = qt_polymul_host(g_multi_ctx[set][gidx], x + lo * p.n, y + lo * p.n, z + lo * p.n, hi - lo);
             rcs[gidx] = rc;
         });
     }
     for (auto& t : th) t.join();
     for (int rc : rcs)
         if (rc) return rc;
+    return 0;
+}
+
+int qt_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_multi_mutex);
+    for (int s = 0; s < NUM_SETS; s++)
+        for (int d = 0; d < 64; d++)
+            if (g_multi_ctx[s][d]) { qt_destroy(g_multi_ctx[s][d]); g_multi_ctx[s][d] = nullptr; }
     return 0;
 }
 

@@ -1,5 +1,6 @@
-// reference_api.cpp — the reference's harness-level operators (main.cuh:61-70) over the C ABI.
-// Host-only C++: no CUDA headers, everything goes through libqtesla_b200.so.
+// qt_reference_api.cpp — the reference's harness-level operators (main.cuh:61-70) over the C ABI
+// (include/qtesla_b200_reference_api.h).  Host-only C++: no CUDA headers, only qt_* calls; built into
+// libqtesla_b200.so so that a maintainer links one library.
 #include "../../include/qtesla_b200_reference_api.h"
 
 #include <chrono>

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "qt_polymul_host": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
     "qt_polymul_host_multi": (C.c_int, [C.c_int, _vp, _vp, _vp, _sz, C.c_int]),
     "qt_nussbaumer_host": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.c_int]),
+    "qt_shutdown": (C.c_int, []),
     "qt_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "qt_kernel_info": (C.c_int, [_vp] + [C.POINTER(C.c_int)] * 5),
 }

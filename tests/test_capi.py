@@ -17,15 +17,18 @@ def sha(a):
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "qtesla_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(qt_[a-z0-9_]+)\s*\(", text)))
+    syms = set()
+    for h in ("qtesla_b200.h", "qtesla_b200_reference_api.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        syms |= set(re.findall(r"\b((?:qt_|test_)[A-Za-z0-9_]+)\s*\(", text))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol(qt):
     L = qt.lib()
     syms = declared_symbols()
-    assert len(syms) >= 25
+    assert len(syms) >= 35 and "test_NTT_GS_CT_nega_gpu" in syms and "qt_polymul" in syms
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/qtesla_b200.h but not exported"
     assert b"sm_100a" in L.qt_version()
