@@ -10,6 +10,22 @@ namespace qt { TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX]; }
 using namespace qt;
 using T = Tile<SET_III>;
 
+// issue-slot competition probe: the forward transform plus EXTRA independent ALU instructions per butterfly
+template <int EXTRA> __device__ __forceinline__ void fwd_rows_padded(uint32_t (&v)[T::E], uint32_t (&d)[8]) {
+#pragma unroll
+    for (uint32_t l = 0; l < T::LB1; l++) {
+        const uint32_t half = T::E >> (l + 1);
+#pragma unroll
+        for (uint32_t i = 0; i < T::E / 2; i++) {
+            const uint32_t g = i / half, j = i % half;
+            T::ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET_III, UNI_FWD>((1u << l) + g));
+#pragma unroll
+            for (int e = 0; e < EXTRA; e++)
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(d[(i + e) & 7]) : "r"(d[(i + e + 3) & 7]));
+        }
+    }
+}
+
 template <int MODE> __global__ void __launch_bounds__(768, 1) k(uint32_t* out, const TwQuad* g_tw, int iters, long long* cyc) {
     extern __shared__ uint4 sm[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(sm);
@@ -18,9 +34,14 @@ template <int MODE> __global__ void __launch_bounds__(768, 1) k(uint32_t* out, c
     const uint32_t lane = threadIdx.x & 31;
     uint32_t v[T::E];
     for (uint32_t r = 0; r < T::E; r++) v[r] = threadIdx.x * 33 + r;
+    uint32_t dmy[8];
+    for (int r = 0; r < 8; r++) dmy[r] = threadIdx.x + r;
     long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
         if (MODE == 0) T::fwd_rows(v);
+        if (MODE == 10) fwd_rows_padded<1>(v, dmy);
+        if (MODE == 11) fwd_rows_padded<2>(v, dmy);
+        if (MODE == 12) fwd_rows_padded<4>(v, dmy);
         if (MODE == 1) T::fwd_cols(v, s_tw + lane);
         if (MODE == 2) { T::fwd_rows(v); T::fwd_cols(v, s_tw + lane); }
         if (MODE == 3) { T::inv_cols(v, s_tw + 31 - lane); T::inv_rows<UNI_INV_FUSED>(v); }
@@ -29,6 +50,7 @@ template <int MODE> __global__ void __launch_bounds__(768, 1) k(uint32_t* out, c
     long long t1 = clock64();
     uint32_t s = 0;
     for (uint32_t r = 0; r < T::E; r++) s += v[r];
+    for (int r = 0; r < 8; r++) s += dmy[r];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -64,6 +86,9 @@ int main() {
         run<2>(nm, 160, p.multiProcessorCount, out, tw, cyc);
     }
     g_threads = 512;
+    run<10>("fwd_rows + 1 extra ALU instr per butterfly (3 non-FMA per butterfly)", 80, p.multiProcessorCount, out, tw, cyc);
+    run<11>("fwd_rows + 2 extra ALU instr per butterfly (4 non-FMA per butterfly)", 80, p.multiProcessorCount, out, tw, cyc);
+    run<12>("fwd_rows + 4 extra ALU instr per butterfly (6 non-FMA per butterfly)", 80, p.multiProcessorCount, out, tw, cyc);
     run<0>("fwd_rows (80 butterflies, uniform twiddles)", 80, p.multiProcessorCount, out, tw, cyc);
     run<1>("fwd_cols (80 butterflies, smem twiddles)", 80, p.multiProcessorCount, out, tw, cyc);
     run<2>("forward transform (160)", 160, p.multiProcessorCount, out, tw, cyc);
