@@ -53,6 +53,7 @@ struct qt_ctx {
     cudaStream_t pipe_stream[PIPE] = {nullptr, nullptr, nullptr};
     uint32_t* pipe_buf[PIPE] = {nullptr, nullptr, nullptr};  // x | y per slot, z overwrites x
     size_t pipe_polys = 0;
+    bool pipe_ready = false;
 };
 
 namespace {
@@ -206,8 +207,18 @@ template <int SET> int launch_bitrev(qt_ctx* c, const uint32_t* in, uint32_t* ou
      : (c)->set == SET_P_I   ? fn<SET_P_I>(__VA_ARGS__)          \
                              : fn<SET_P_III>(__VA_ARGS__))
 
+void release_pipe(qt_ctx* c) {
+    for (int i = 0; i < qt_ctx::PIPE; i++) {
+        if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
+        if (c->pipe_stream[i]) cudaStreamDestroy(c->pipe_stream[i]);
+        c->pipe_buf[i] = nullptr;
+        c->pipe_stream[i] = nullptr;
+    }
+    c->pipe_ready = false;
+}
+
 int ensure_pipe(qt_ctx* c) {
-    if (c->pipe_buf[0]) return 0;
+    if (c->pipe_ready) return 0;
     // chunk: 4096 polynomials of n=1024 (16 MiB per operand) — large enough for PCIe efficiency,
     // small enough that three slots overlap H2D, compute and D2H
     c->pipe_polys = (size_t)(4u << 20) / c->p.n;
@@ -216,9 +227,14 @@ int ensure_pipe(qt_ctx* c) {
         if (w >= c->p.n) c->pipe_polys = w / c->p.n;
     }
     for (int i = 0; i < qt_ctx::PIPE; i++) {
-        QT_CUDA(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));
-        QT_CUDA(cudaMalloc(&c->pipe_buf[i], 2 * c->pipe_polys * c->p.n * sizeof(uint32_t)));
+        cudaError_t e = cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&c->pipe_buf[i], 2 * c->pipe_polys * c->p.n * sizeof(uint32_t));
+        if (e != cudaSuccess) {  // leave no half-built pipeline behind
+            release_pipe(c);
+            return (int)e;
+        }
     }
+    c->pipe_ready = true;
     return 0;
 }
 
@@ -301,10 +317,7 @@ int qt_create(int set, int device, qt_ctx** out) {
 int qt_destroy(qt_ctx* c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
-    for (int i = 0; i < qt_ctx::PIPE; i++) {
-        if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
-        if (c->pipe_stream[i]) cudaStreamDestroy(c->pipe_stream[i]);
-    }
+    release_pipe(c);
     if (c->d_lane_fwd) cudaFree(c->d_lane_fwd);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -431,23 +444,28 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
     const size_t n = c->p.n, chunk = c->pipe_polys;
     size_t done = 0;
     int slot = 0;
-    while (done < B) {
+    while (done < B && !rc) {
         const size_t cnt = std::min(chunk, B - done);
         const size_t bytes = cnt * n * sizeof(uint32_t);
         cudaStream_t s = c->pipe_stream[slot];
         uint32_t* dx = c->pipe_buf[slot];
         uint32_t* dy = dx + chunk * n;
-        QT_CUDA(cudaMemcpyAsync(dx, x + done * n, bytes, cudaMemcpyHostToDevice, s));
-        QT_CUDA(cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s));
-        if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
-        else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, s); if (!rc) c->launches++; }
-        if (rc) return rc;
-        QT_CUDA(cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s));
+        rc = (int)cudaMemcpyAsync(dx, x + done * n, bytes, cudaMemcpyHostToDevice, s);
+        if (!rc) rc = (int)cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s);
+        if (!rc) {
+            if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
+            else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, s); if (!rc) c->launches++; }
+        }
+        if (!rc) rc = (int)cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s);
         done += cnt;
         slot = (slot + 1) % qt_ctx::PIPE;
     }
-    for (int i = 0; i < qt_ctx::PIPE; i++) QT_CUDA(cudaStreamSynchronize(c->pipe_stream[i]));
-    return 0;
+    // always drain: the caller's buffers must not be touched after we return, error or not
+    for (int i = 0; i < qt_ctx::PIPE; i++) {
+        const cudaError_t e = cudaStreamSynchronize(c->pipe_stream[i]);
+        if (!rc && e != cudaSuccess) rc = (int)e;
+    }
+    return rc;
 }
 
 int qt_polymul_host(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B) {

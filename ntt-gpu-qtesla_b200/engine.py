@@ -146,7 +146,11 @@ class Engine:
             lib().qt_destroy(self._h)
             self._h = _vp()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the library may already be gone
+            pass
 
     def __enter__(self):
         return self
