@@ -282,7 +282,7 @@ template <int SET, int RING> struct NussWarp {
     static constexpr uint32_t M = K::M, LOGM = K::LOGM, ROWS = K::ROWS, Q = K::Q;
     static constexpr uint32_t RS = 33;                                   // row stride in shared memory
     static constexpr uint32_t WARP_WORDS = 2 * ROWS * RS;                // X rows then Y rows
-    static constexpr uint32_t WARPS = 8;
+    static constexpr uint32_t WARPS = 12;  // 12 x 16.9 KiB of rows, <= 170 registers: one CTA per SM
     static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_WORDS * sizeof(uint32_t);
     static constexpr uint32_t RPL = ROWS / 32;                           // rows per lane in the product phase
     // terms a 64-bit accumulator may take before a Montgomery reduction: sum < q * 2^32
