@@ -41,7 +41,7 @@ struct qt_ctx {
     RtParams p{};
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    TwQuad* d_lane_fwd = nullptr;  // merged-psi per-lane twiddles; the inverse reads it mirrored
+    TwQuad* d_tab[2] = {nullptr, nullptr};  // kernel table blocks: [0] plain output scale, [1] fused (x 2^32)
     int num_sms = 0;
     int grid_fused = 0, grid_fwd = 0, grid_inv = 0, grid_nuss = 0, grid_tma = 0;
     int occ_fused = 0, occ_tma = 0, tma_warps = 0;
@@ -114,9 +114,11 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
 int upload_tables(qt_ctx* c) {
     HostTables T;
     build_tables(c->set, &T);
-    const size_t quads = T.lane_fwd.size();
-    QT_CUDA(cudaMalloc(&c->d_lane_fwd, quads * sizeof(TwQuad)));
-    QT_CUDA(cudaMemcpy(c->d_lane_fwd, T.lane_fwd.data(), quads * sizeof(TwQuad), cudaMemcpyHostToDevice));
+    for (int k = 0; k < 2; k++) {
+        const size_t bytes = T.block[k].size() * sizeof(TwQuad);
+        QT_CUDA(cudaMalloc(&c->d_tab[k], bytes));
+        QT_CUDA(cudaMemcpy(c->d_tab[k], T.block[k].data(), bytes, cudaMemcpyHostToDevice));
+    }
     {
         std::lock_guard<std::mutex> lk(g_uni_mutex);
         memcpy(h_uni[c->set], T.uni, sizeof(T.uni));
@@ -148,10 +150,10 @@ template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32
     if (tma)
         k_polymul_tma<SET><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS)),
                              TmaCfg<SET>::WARPS * 32, c->smem_tma, s>>>(
-            x, y, z, B, c->d_lane_fwd);
+            x, y, z, B, c->d_tab[1]);
     else
         k_polymul<SET><<<grid_for(c->grid_fused, tiles), WARPS_PER_CTA * 32, c->smem_fused, s>>>(
-            x, y, z, B, c->d_lane_fwd);
+            x, y, z, B, c->d_tab[1]);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -160,29 +162,29 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
     if (c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
     if ((((uintptr_t)ahat | (uintptr_t)y) & 15) != 0) return QT_ERR_BAD_ARG;  // 128-bit / bulk-copy alignment
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS));
-    if (bcast) k_polymul_ntt<SET, true><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_lane_fwd);
-    else k_polymul_ntt<SET, false><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_lane_fwd);
+    if (bcast) k_polymul_ntt<SET, true><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
+    else k_polymul_ntt<SET, false><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <int SET, bool INV> int launch_ntt_tma(qt_ctx* c, uint32_t* a, size_t B) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS));
-    k_ntt_tma<SET, INV><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(a, B, c->d_lane_fwd);
+    k_ntt_tma<SET, INV><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(a, B, c->d_tab[0]);
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
     if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, false>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
-    k_ntt_forward<SET><<<grid_for(c->grid_fwd, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_fwd);
+    k_ntt_forward<SET><<<grid_for(c->grid_fwd, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_tab[0]);
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <int SET> int launch_inverse(qt_ctx* c, uint32_t* a, size_t B) {
     if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, true>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
-    k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_lane_fwd);
+    k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_tab[0]);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -318,7 +320,8 @@ int qt_destroy(qt_ctx* c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     release_pipe(c);
-    if (c->d_lane_fwd) cudaFree(c->d_lane_fwd);
+    for (int k = 0; k < 2; k++)
+        if (c->d_tab[k]) cudaFree(c->d_tab[k]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;

@@ -31,7 +31,7 @@ template <int SET> struct TmaCfg {
 
 template <int SET> struct KernelShape {
     using T = Tile<SET>;
-    static constexpr size_t TW_QUADS = (size_t)T::SLOT_PAIRS * T::BLOCKS;  // one table serves both directions
+    static constexpr size_t TW_QUADS = T::TABLE_QUADS;  // the kernel's table block (qt_tile.cuh: lane_ptrs)
     static constexpr size_t TW_BYTES = TW_QUADS * sizeof(TwQuad);
     static constexpr size_t BUF_BYTES = (size_t)WARPS_PER_CTA * T::C::TILE_WORDS * sizeof(uint32_t);
     static constexpr size_t SMEM_DIRECT = TW_BYTES + BUF_BYTES;
@@ -59,8 +59,7 @@ k_polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
-    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
-    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
 
     for (size_t tile = (size_t)blockIdx.x * WARPS_PER_CTA + warp; tile < ntiles;
@@ -77,18 +76,18 @@ k_polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const
         __syncwarp();
         T::fwd_rows(vy);
         T::sts_rows(vy, buf, lane);
-        T::fwd_cols(vx, tw_f);
+        T::fwd_cols(vx, P.fwd);
         __syncwarp();
         T::lds_cols(vy, buf, lane);
-        T::fwd_cols(vy, tw_f);
+        T::fwd_cols(vy, P.fwd);
         T::pointwise_mont(vy, vx);
-        T::inv_cols(vy, tw_i);
+        T::inv_cols(vy, P.inv);
         __syncwarp();
         T::sts_cols(vy, buf, lane);
         __syncwarp();
         T::lds_rows(vy, buf, lane);
         __syncwarp();
-        T::template inv_rows<UNI_INV_FUSED>(vy);
+        T::template inv_rows<UNI_INV_FUSED>(vy, P);
         T::store_rows(vy, z + base, lane, valid);
     }
 }
@@ -187,8 +186,7 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
 
-    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
-    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     uint32_t phase = 0;
     for (; tile < ntiles; tile += stride, phase ^= 1) {
         const size_t base = tile * T::C::TILE_WORDS;
@@ -206,7 +204,7 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
             T::sts_rows(v, st, lane);
             __syncwarp();
             T::lds_cols(v, st, lane);
-            T::fwd_cols(v, tw_f);
+            T::fwd_cols(v, P.fwd);
             if (op == 0) {
                 __syncwarp();             // every lane has read its columns before A is overwritten
                 T::sts_cols(v, A, lane);  // stash NTT(x); each lane reads back only what it wrote
@@ -216,14 +214,14 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
         fence_proxy_async();
         __syncwarp();                     // A is free: fetch the next tile's x into it
         if (more && lane == 0) issue(x, A, bar_a, tile + stride);
-        T::inv_cols(v, tw_i);
+        T::inv_cols(v, P.inv);
         T::sts_cols(v, B, lane);          // (all lanes passed the __syncwarp above after reading B)
         __syncwarp();
         T::lds_rows(v, B, lane);
         fence_proxy_async();
         __syncwarp();                     // B is free: fetch the next tile's y into it
         if (more && lane == 0) issue(y, B, bar_b, tile + stride);
-        T::template inv_rows<UNI_INV_FUSED>(v);
+        T::template inv_rows<UNI_INV_FUSED>(v, P);
         T::store_rows(v, z + base, lane, valid);
     }
 }
@@ -269,8 +267,7 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
     }
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
-    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
-    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     uint32_t phase = 0;
     for (; tile < ntiles; tile += stride, phase ^= 1) {
         const size_t base = tile * T::C::TILE_WORDS;
@@ -288,16 +285,16 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
         T::sts_rows(v, B, lane);
         __syncwarp();
         T::lds_cols(v, B, lane);
-        T::fwd_cols(v, tw_f);
+        T::fwd_cols(v, P.fwd);
 #pragma unroll
         for (uint32_t c = 0; c < T::E / 4; c++) {
             const uint4 u = __ldg(ah + c);
             const uint32_t b[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++)
-                v[4 * c + k] = T::LAZY ? T::mul_mont(v[4 * c + k], b[k]) : T::mul_mont(T::csub(v[4 * c + k], T::TWO_Q), b[k]);
+                v[4 * c + k] = T::pw_canonical(v[4 * c + k], b[k]);
         }
-        T::inv_cols(v, tw_i);
+        T::inv_cols(v, P.inv);
         __syncwarp();
         T::sts_cols(v, B, lane);
         __syncwarp();
@@ -305,7 +302,7 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
         fence_proxy_async();
         __syncwarp();
         if (more && lane == 0) issue(tile + stride);
-        T::template inv_rows<UNI_INV_FUSED>(v);
+        T::template inv_rows<UNI_INV_FUSED>(v, P);
         T::store_rows(v, z + base, lane, valid);
     }
 }
@@ -323,7 +320,7 @@ k_ntt_forward(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
-    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     for (size_t tile = (size_t)blockIdx.x * WARPS_PER_CTA + warp; tile < ntiles;
          tile += (size_t)gridDim.x * WARPS_PER_CTA) {
@@ -335,7 +332,7 @@ k_ntt_forward(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
         T::sts_rows(v, buf, lane);
         __syncwarp();
         T::lds_cols(v, buf, lane);
-        T::fwd_cols(v, tw_f);
+        T::fwd_cols(v, P.fwd);
         T::canon_fwd(v);
         __syncwarp();
         T::sts_cols(v, buf, lane);  // re-layout only, so that the global store is coalesced
@@ -359,7 +356,7 @@ k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
-    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     for (size_t tile = (size_t)blockIdx.x * WARPS_PER_CTA + warp; tile < ntiles;
          tile += (size_t)gridDim.x * WARPS_PER_CTA) {
@@ -370,13 +367,13 @@ k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
         T::sts_rows(v, buf, lane);
         __syncwarp();
         T::lds_cols(v, buf, lane);
-        T::inv_cols(v, tw_i);
+        T::inv_cols(v, P.inv);
         __syncwarp();
         T::sts_cols(v, buf, lane);
         __syncwarp();
         T::lds_rows(v, buf, lane);
         __syncwarp();
-        T::template inv_rows<UNI_INV_PLAIN>(v);
+        T::template inv_rows<UNI_INV_PLAIN>(v, P);
         T::store_rows(v, a + base, lane, valid);
     }
 }
@@ -422,8 +419,7 @@ k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     }
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
-    const TwQuad* tw_f = s_tw + (lane % T::BLOCKS);
-    const TwQuad* tw_i = s_tw + (T::BLOCKS - 1 - lane % T::BLOCKS);
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     for (uint32_t k = 0; tile < ntiles; tile += stride, k++) {
         uint32_t* cur = buf0 + (k & 1) * G::WORDS;
         uint32_t* nxt = buf0 + ((k & 1) ^ 1) * G::WORDS;
@@ -444,13 +440,13 @@ k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
             T::sts_rows(v, cur, lane);
             __syncwarp();
             T::lds_cols(v, cur, lane);
-            T::fwd_cols(v, tw_f);
+            T::fwd_cols(v, P.fwd);
             T::canon_fwd(v);
         } else {
             T::sts_rows(v, cur, lane);  // re-layout: NTT-domain data is consumed in the cols layout
             __syncwarp();
             T::lds_cols(v, cur, lane);
-            T::inv_cols(v, tw_i);
+            T::inv_cols(v, P.inv);
         }
         __syncwarp();
         T::sts_cols(v, cur, lane);
@@ -458,7 +454,7 @@ k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
         T::lds_rows(v, cur, lane);
         fence_proxy_async();
         __syncwarp();
-        if (INVERSE) T::template inv_rows<UNI_INV_PLAIN>(v);
+        if (INVERSE) T::template inv_rows<UNI_INV_PLAIN>(v, P);
         T::store_rows(v, a + base, lane, valid);
     }
 }

@@ -23,21 +23,41 @@ struct HostTables {
     RtParams p;
     // reference drop-in tables, n words each
     std::vector<uint32_t> bitrev, Phi, invPhi, tf0, ti0;
-    // uniform (lane-independent) twiddles of the strided pass: index k in [1, 2^LB1);
-    // for the inverse kinds index 0 holds the output scale K and index 1 is pre-multiplied by K
+    // uniform (lane-independent) twiddles, index k in [1, 2^LB1).
+    //   UNI_FWD            : merged zetas of the forward rows pass, zeta[k] = psi^brv(k)
+    //   UNI_INV_* (Harvey) : inverse zetas of the rows pass; index 0 = output scale K, index 1 pre-multiplied by K
+    //   UNI_INV_* (LAZY)   : cyclic DIT twiddles of the cols pass: index l + j = omega^-(j*n/(2l)), l = 2^s
     TwPair uni[UNI_KINDS][UNI_MAX];
-    // per-lane twiddles of the contiguous pass: [pair][block], block = n/E lanes
-    std::vector<TwQuad> lane_fwd;  // the inverse pass reads the same table mirrored (qt_tile.cuh inv_cols)
-    uint32_t lane_blocks;  // n / E
+    // kernel table blocks (one per output-scale kind): [fwd per-lane][LAZY: inverse per-lane][LAZY: scale]
+    std::vector<TwQuad> block[2];  // 0: plain scale n^-1 psi^-i (unfused inverse), 1: fused scale (x 2^32)
+    uint32_t fwd_quads, inv_quads, scale_quads;
 };
 
+// LAZY sets store twiddles for the SIGNED Shoup product: w centred in (-q/2, q/2] as a two's-complement word,
+// companion floor(w * 2^32 / q) as a signed word.  Harvey sets: w in [0,q), companion floor(w*2^32/q).
 inline uint32_t shoup(uint32_t w, uint32_t q) { return (uint32_t)(((uint64_t)w << 32) / q); }
+inline TwPair tw_unsigned(uint32_t w, uint32_t q) { return TwPair{w, shoup(w, q)}; }
+inline TwPair tw_signed(uint32_t w, uint32_t q) {
+    const int64_t wc = (w > q / 2) ? (int64_t)w - (int64_t)q : (int64_t)w;
+    const int64_t num = wc * (int64_t)(1ll << 32);
+    int64_t fl = num / (int64_t)q;
+    if (num % (int64_t)q != 0 && num < 0) fl -= 1;  // floor division
+    return TwPair{(uint32_t)(int32_t)wc, (uint32_t)(int32_t)fl};
+}
+
+inline void put_slot(std::vector<TwQuad>& v, size_t base, uint32_t slot, uint32_t stride, uint32_t lane, TwPair t) {
+    TwQuad& qd = v[base + (size_t)(slot / 2) * stride + lane];
+    if (slot & 1) { qd.w1 = t.w; qd.ws1 = t.ws; }
+    else          { qd.w0 = t.w; qd.ws0 = t.ws; }
+}
 
 inline void build_tables(int set, HostTables* T) {
     RtParams p;
     rt_params(set, &p);
     T->p = p;
     const uint32_t n = p.n, q = p.q;
+    const bool lazy = p.lazy != 0;
+    auto mk = [&](uint32_t w) { return lazy ? tw_signed(w, q) : tw_unsigned(w, q); };
     T->bitrev.resize(n); T->Phi.resize(n); T->invPhi.resize(n); T->tf0.resize(n); T->ti0.resize(n);
     std::vector<uint32_t> psi_pow(2 * n);  // psi^e, e in [0,2n)
     psi_pow[0] = 1;
@@ -56,33 +76,59 @@ inline void build_tables(int set, HostTables* T) {
     for (int kind = 0; kind < UNI_KINDS; kind++)
         for (int k = 0; k < UNI_MAX; k++) T->uni[kind][k] = TwPair{0, 0};
     const uint32_t K_plain = p.n_inv;
-    const uint32_t K_fused = c_mulmod(p.n_inv, p.r_modq, q);  // absorbs the pointwise Montgomery R^-1
-    for (uint32_t k = 1; k < uni; k++) {
-        uint32_t f = zf(k), ip = zi(k), ifu = zi(k);
-        if (k == 1) { ip = c_mulmod(ip, K_plain, q); ifu = c_mulmod(ifu, K_fused, q); }
-        T->uni[UNI_FWD][k] = TwPair{f, shoup(f, q)};
-        T->uni[UNI_INV_PLAIN][k] = TwPair{ip, shoup(ip, q)};
-        T->uni[UNI_INV_FUSED][k] = TwPair{ifu, shoup(ifu, q)};
+    const uint32_t K_fused = c_mulmod(p.n_inv, p.r_modq, q);  // absorbs the pointwise Montgomery 2^-32
+    for (uint32_t k = 1; k < uni; k++) T->uni[UNI_FWD][k] = mk(zf(k));
+    if (!lazy) {
+        for (uint32_t k = 1; k < uni; k++) {
+            uint32_t ip = zi(k), ifu = zi(k);
+            if (k == 1) { ip = c_mulmod(ip, K_plain, q); ifu = c_mulmod(ifu, K_fused, q); }
+            T->uni[UNI_INV_PLAIN][k] = tw_unsigned(ip, q);
+            T->uni[UNI_INV_FUSED][k] = tw_unsigned(ifu, q);
+        }
+        T->uni[UNI_INV_PLAIN][0] = tw_unsigned(K_plain, q);
+        T->uni[UNI_INV_FUSED][0] = tw_unsigned(K_fused, q);
+    } else {
+        // cyclic DIT (radix2INTT, NTT.cu:1478-1493): level s, half size l = 2^s, position j < l: ti0[j * n/(2l)]
+        for (uint32_t s = 0; s < p.lb2; s++) {
+            const uint32_t l = 1u << s;
+            for (uint32_t j = 0; j < l; j++)
+                T->uni[UNI_INV_PLAIN][l + j] = T->uni[UNI_INV_FUSED][l + j] = tw_signed(T->ti0[j * (n / (2 * l))], q);
+        }
     }
-    T->uni[UNI_INV_PLAIN][0] = TwPair{K_plain, shoup(K_plain, q)};
-    T->uni[UNI_INV_FUSED][0] = TwPair{K_fused, shoup(K_fused, q)};
-    // per-lane tables.  Thread-block j' (first element E*j') at level l uses zeta indices
-    // 2^l + j'*G_l + g, g in [0,G_l), G_l = E >> (logn - l); slots enumerate (l, g), l ascending.
-    const uint32_t blocks = n / p.E;
-    T->lane_blocks = blocks;
-    T->lane_fwd.assign((size_t)p.slot_pairs * blocks, TwQuad{0, 0, 0, 0});
-    for (uint32_t jb = 0; jb < blocks; jb++) {
-        uint32_t slot = 0;
-        for (uint32_t l = p.lb1; l < p.logn; l++) {
-            const uint32_t G = p.E >> (p.logn - l);
-            for (uint32_t g = 0; g < G; g++, slot++) {
-                const uint32_t k = (1u << l) + jb * G + g;
-                const uint32_t f = zf(k);
-                TwQuad& qf = T->lane_fwd[(size_t)(slot / 2) * blocks + jb];
-                if (slot & 1) { qf.w1 = f; qf.ws1 = shoup(f, q); }
-                else          { qf.w0 = f; qf.ws0 = shoup(f, q); }
+    // ---- kernel table blocks -----------------------------------------------------------------------
+    const uint32_t blocks = n / p.E;                 // lane blocks of the forward cols pass
+    const uint32_t lpp = 32 / p.ppw;                 // lanes per polynomial (rows layout)
+    T->fwd_quads = p.slot_pairs * blocks;
+    T->inv_quads = lazy ? ((p.E - 1 + 1) / 2) * lpp : 0;
+    T->scale_quads = lazy ? (p.E / 2) * lpp : 0;
+    for (int kind = 0; kind < 2; kind++) {
+        std::vector<TwQuad>& B = T->block[kind];
+        B.assign((size_t)T->fwd_quads + T->inv_quads + T->scale_quads, TwQuad{0, 0, 0, 0});
+        // forward per-lane table: block jb (first element E*jb) at level l uses zeta indices
+        // 2^l + jb*G_l + g, G_l = E >> (logn - l); slots enumerate (l, g), l ascending
+        for (uint32_t jb = 0; jb < blocks; jb++) {
+            uint32_t slot = 0;
+            for (uint32_t l = p.lb1; l < p.logn; l++) {
+                const uint32_t G = p.E >> (p.logn - l);
+                for (uint32_t g = 0; g < G; g++, slot++) put_slot(B, 0, slot, blocks, jb, mk(zf((1u << l) + jb * G + g)));
             }
         }
+        if (!lazy) continue;
+        // inverse rows pass (DIT levels s = lb2 .. logn-1): lane j holds positions j + lpp*r; level with
+        // half size l = lpp*G pairs registers (r, r+G), twiddle ti0[(j + lpp*g) * n/(2l)], slot G-1+g
+        for (uint32_t j = 0; j < lpp; j++)
+            for (uint32_t k = 0; k < p.lb1; k++) {
+                const uint32_t G = 1u << k, l = lpp * G;
+                for (uint32_t g = 0; g < G; g++)
+                    put_slot(B, T->fwd_quads, G - 1 + g, lpp, j, tw_signed(T->ti0[((j + lpp * g) * (n / (2 * l))) % n], q));
+            }
+        // output scale of coefficient i = j + lpp*r: n^-1 psi^-i (= invPhi[i]), fused kind times 2^32
+        for (uint32_t j = 0; j < lpp; j++)
+            for (uint32_t r = 0; r < p.E; r++) {
+                uint32_t sc = T->invPhi[j + lpp * r];
+                if (kind == 1) sc = c_mulmod(sc, p.r_modq, q);
+                put_slot(B, (size_t)T->fwd_quads + T->inv_quads, r, lpp, j, tw_signed(sc, q));
+            }
     }
 }
 

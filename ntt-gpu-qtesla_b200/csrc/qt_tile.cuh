@@ -17,11 +17,12 @@
 //                         twiddles are identical for all lanes (constant-bank operands);
 //      "cols" layout : register r of lane L holds tile word E*L + r (E consecutive coefficients)
 //                      -> the remaining levels are thread-local; twiddles are per lane (shared memory).
-//  * Modular arithmetic: Shoup multiplication by precomputed constants (1 mul.hi + 2 mul.lo),
-//    result in [0,2q).  For q < 2^25 ("LAZY") butterflies carry no correction at all: the forward
-//    transform grows values by 2q per level (< 21q), the inverse doubles per level with one
-//    mid-transform Barrett fold of the few registers that could overflow.  For the 29/30-bit moduli
-//    Harvey's [0,4q) butterflies are used.  The single final store is canonical in [0,q).
+//  * Modular arithmetic: Shoup multiplication by precomputed constants (1 mul.hi + 2 mul.lo).
+//    q < 2^25 ("LAZY"): signed residues, no correction anywhere; the Cooley-Tukey butterfly is
+//    3 multiply-pipe instructions + 1 add (the sum rides on the multiply-add), and the inverse is a
+//    cyclic decimation-in-time transform (also Cooley-Tukey butterflies, 31 of 160 per thread free of
+//    multiplications) followed by the reference's own invPhi scale.  29/30-bit moduli: Harvey's
+//    [0,4q) butterflies, merged Gentleman-Sande inverse.  The single final store is canonical.
 //
 // Everything here is __host__ __device__ so that tests/emu can execute the identical index
 // arithmetic and 32-bit wrap-around behaviour lane by lane on a CPU (test infrastructure only).
@@ -66,6 +67,13 @@ QT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+QT_HD int32_t mulhi32s(uint32_t a, uint32_t b) {  // signed high word of two two's-complement patterns
+#if defined(__CUDA_ARCH__)
+    return __mulhi((int)a, (int)b);
+#else
+    return (int32_t)(((int64_t)(int32_t)a * (int64_t)(int32_t)b) >> 32);
+#endif
+}
 QT_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 struct alignas(16) U4 { uint32_t x, y, z, w; };  // 128-bit shared-memory access unit
@@ -79,31 +87,32 @@ template <int SET> struct Tile {
     static constexpr bool LAZY = C::LAZY;
     static constexpr uint32_t TWO_Q = 2 * Q;
 
-    // ---- lazy-reduction budget (all bounds in units of q) -------------------------------------
-    static constexpr uint32_t QCAP = (uint32_t)(0xFFFFFFFFull / Q);  // values < QCAP*q fit 32 bits
-    static constexpr uint32_t FWD_BOUND = LAZY ? (2 * LOGN + 1) : 4;  // forward output < FWD_BOUND*q
-    // largest power of two MID with MID * 2^LB1 <= QCAP: bound allowed when the rows inverse starts
-    static QT_CONSTEXPR_HD uint32_t mid_bound() {
-        uint32_t m = 1;
-        while ((uint64_t)(2 * m) << LB1 <= QCAP) m *= 2;
-        return m;
-    }
-    static constexpr uint32_t MID = LAZY ? mid_bound() : 2;
-    static_assert(!LAZY || (uint64_t)FWD_BOUND * FWD_BOUND * Q < (1ull << 32),
-                  "pointwise Montgomery needs a*b < q*2^32");
-    static_assert(!LAZY || ((uint64_t)(2u << LB2)) <= QCAP, "cols inverse must fit 32 bits");
-    static_assert(!LAZY || MID >= 2, "no room for the lazy inverse");
-    // bound of register r after the cols inverse pass (inputs < 2q, a-path doubles, b-path -> 2q)
-    static QT_CONSTEXPR_HD uint32_t bound_after_cols_inverse(uint32_t r) {
-        uint32_t low = r & ((1u << LB2) - 1);
-        if (low == 0) return 2u << LB2;
-        uint32_t h = 0;
-        while ((low >> (h + 1)) != 0) h++;
-        return 2u << (LB2 - 1 - h);
+    // ---- shared-memory table block of one kernel ---------------------------------------------------
+    // [forward per-lane twiddles][LAZY only: inverse per-lane twiddles][LAZY only: output scale]
+    static constexpr uint32_t TW_QUADS = SLOT_PAIRS * BLOCKS;
+    static constexpr uint32_t INV_SLOTS = E - 1;                      // rows levels of the DIT inverse: 1+2+..+E/2
+    static constexpr uint32_t INV_QUADS = LAZY ? ((INV_SLOTS + 1) / 2) * LPP : 0;
+    static constexpr uint32_t SCALE_QUADS = LAZY ? (E / 2) * LPP : 0;
+    static constexpr uint32_t TABLE_QUADS = TW_QUADS + INV_QUADS + SCALE_QUADS;
+    struct LanePtrs { const TwQuad *fwd, *inv, *scale; };
+    static QT_HD LanePtrs lane_ptrs(const TwQuad* tab, uint32_t lane) {
+        if (LAZY) return LanePtrs{tab + lane % BLOCKS, tab + TW_QUADS + lane % LPP, tab + TW_QUADS + INV_QUADS + lane % LPP};
+        return LanePtrs{tab + lane % BLOCKS, tab + (BLOCKS - 1 - lane % BLOCKS), nullptr};  // Harvey sets: mirrored table
     }
 
+    // ---- range bookkeeping ------------------------------------------------------------------------------
+    static constexpr uint32_t QCAP = (uint32_t)(0xFFFFFFFFull / Q);  // values < QCAP*q fit 32 bits
+    // LAZY ("signed lazy", q < 2^25): values are two's-complement residues.  A signed Shoup product lies in
+    // [-q/2, 3q/2), so a Cooley-Tukey level moves |v| by at most 1.5 q and NO correction is ever needed:
+    //   forward : |v| < (1 + 1.5 log2 n) q <= 17.5 q
+    //   inverse : decimation-in-time; its first LB2 levels contain the multiplication-free butterflies
+    //             (twiddle 1), which may double: |v| < 2^LB2 q, then + 1.5 q per remaining level
+    static_assert(!LAZY || (uint64_t)(2 + 3 * LOGN) * Q < (1ull << 32), "forward range");           // 2*(1+1.5 logn) q < 2^32
+    static_assert(!LAZY || ((uint64_t)(4u << LB2) + 3 * LB1) * Q < (1ull << 32), "inverse range");  // (2*2^LB2 + 1.5 LB1) q < 2^31
+    static constexpr uint32_t FWD_BOUND = LAZY ? (2 * LOGN + 1) : 4;  // |forward output| < FWD_BOUND*q
+
     // ---- modular arithmetic ---------------------------------------------------------------------
-    // y*w mod q for ANY 32-bit y, result in [0,2q)   (Shoup / Harvey)
+    // y*w mod q for ANY 32-bit y, result in [0,2q)   (Shoup / Harvey), w with floor(w*2^32/q)
     static QT_HD uint32_t mul_shoup(uint32_t y, TwPair t) { return y * t.w - mulhi32(y, t.ws) * Q; }
     // a*b*2^-32 mod q, result in [0,2q); requires a*b < q*2^32
     static QT_HD uint32_t mul_mont(uint32_t a, uint32_t b) {
@@ -114,19 +123,40 @@ template <int SET> struct Tile {
     static QT_HD uint32_t fold2q(uint32_t a) { return a - mulhi32(a, C::MU32) * Q; }  // any a -> [0,2q)
     static QT_HD uint32_t csub(uint32_t a, uint32_t m) { return umin32(a, a - m); }    // [0,2m) -> [0,m)
 
+    // signed variants: operands are two's-complement bit patterns; t = (w centred in (-q/2, q/2],
+    // floor(w*2^32/q) as a signed word).  Result in [-q/2, 3q/2) for any |y| < 2^31.
+    static QT_HD uint32_t smul_shoup(uint32_t y, TwPair t) { return y * t.w - (uint32_t)mulhi32s(y, t.ws) * Q; }
+    // signed Montgomery: a*b*2^-32 mod q, |result| < q/2 + |a*b|/2^32 + 1
+    static QT_HD uint32_t smul_mont(uint32_t a, uint32_t b) {
+        const int64_t t = (int64_t)(int32_t)a * (int32_t)b;
+        const uint32_t m = (uint32_t)t * (0u - C::QINV_NEG);  // lo(t) * q^-1: t - m*q has a zero low word
+        return (uint32_t)(t >> 32) - (uint32_t)mulhi32s(m, Q);
+    }
+    // [-q/2, 3q/2) -> [0, q)
+    static QT_HD uint32_t scanon(uint32_t r) { return csub(umin32(r, r + Q), Q); }
+
     // forward (Cooley-Tukey) butterfly: (x, y) -> (x + w y, x - w y)
     static QT_HD void ct(uint32_t& x, uint32_t& y, TwPair t) {
-        uint32_t wy = mul_shoup(y, t);
-        uint32_t xx = LAZY ? x : csub(x, TWO_Q);
-        x = xx + wy;
-        y = xx - wy + TWO_Q;
+        if (LAZY) {
+            // 3 multiply-pipe instructions + ONE add: the sum rides on the multiply-add's addend,
+            // the difference is 2x - x'
+            const uint32_t hi = (uint32_t)mulhi32s(y, t.ws);
+            const uint32_t u = y * t.w + x;
+            const uint32_t xn = u - hi * Q;
+            y = x + x - xn;
+            x = xn;
+        } else {
+            const uint32_t wy = mul_shoup(y, t);
+            const uint32_t xx = csub(x, TWO_Q);
+            x = xx + wy;
+            y = xx - wy + TWO_Q;
+        }
     }
-    // inverse (Gentleman-Sande) butterfly: (a, b) -> (a + b, (a - b) w); inputs < bound*q
-    static QT_HD void gs(uint32_t& a, uint32_t& b, TwPair t, uint32_t bound) {
-        uint32_t s = a + b;
-        uint32_t d = a - b + bound * Q;
-        a = LAZY ? s : csub(s, TWO_Q);
-        b = mul_shoup(d, t);
+    // inverse (Gentleman-Sande) butterfly of the Harvey sets: (a, b) -> (a + b, (b - a) w'), in/out < 2q
+    static QT_HD void gs(uint32_t& a, uint32_t& b, TwPair t_mirror) {
+        const uint32_t s_ = a + b, d = b - a + TWO_Q;
+        a = csub(s_, TWO_Q);
+        b = mul_shoup(d, t_mirror);
     }
 
     // ---- transforms on one lane's registers ---------------------------------------------------
@@ -143,12 +173,12 @@ template <int SET> struct Tile {
         }
     }
 
-    static QT_HD TwPair lane_slot(const TwQuad* tw, uint32_t slot) {
-        const TwQuad qd = tw[(size_t)(slot >> 1) * BLOCKS];
+    static QT_HD TwPair lane_slot(const TwQuad* tw, uint32_t slot, uint32_t stride) {
+        const TwQuad qd = tw[(size_t)(slot >> 1) * stride];
         return (slot & 1) ? TwPair{qd.w1, qd.ws1} : TwPair{qd.w0, qd.ws0};
     }
 
-    // cols layout, forward levels LB1..LOGN-1 (register distance N>>(l+1)); tw = &lane_fwd[block]
+    // cols layout, forward levels LB1..LOGN-1 (register distance N>>(l+1)); tw = lane_ptrs().fwd
     static QT_HD void fwd_cols(uint32_t (&v)[E], const TwQuad* tw) {
 #pragma unroll
         for (uint32_t k = 0; k < LB2; k++) {
@@ -157,91 +187,123 @@ template <int SET> struct Tile {
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t g = i / half, j = i % half;
-                ct(v[2 * g * half + j], v[2 * g * half + j + half], lane_slot(tw, G - G0 + g));
+                ct(v[2 * g * half + j], v[2 * g * half + j + half], lane_slot(tw, G - G0 + g, BLOCKS));
             }
         }
     }
 
-    // cols layout, inverse levels LOGN-1..LB1; inputs < 2q.  Ends with the mid-transform fold.
-    // No inverse table: zeta[k]^-1 = -zeta[k'] with k' the mirror of k inside its level
-    // (psi^-e = -psi^(n-e)), so (a-b)*zeta^-1 = (b-a)*zeta[k'].  The mirror of lane-block j, group g
-    // is lane-block BLOCKS-1-j, group G-1-g: `tw_mirror` = &lane_fwd[BLOCKS-1-block].
-    static QT_HD void inv_cols(uint32_t (&v)[E], const TwQuad* tw_mirror) {
-#pragma unroll
-        for (uint32_t k = 0; k < LB2; k++) {
-            const uint32_t half = 1u << k;
-            const uint32_t G = E / (2 * half);
-            const uint32_t bound = LAZY ? (2u << k) : 2u;
-#pragma unroll
-            for (uint32_t i = 0; i < E / 2; i++) {
-                const uint32_t g = i / half, j = i % half;
-                uint32_t& a = v[2 * g * half + j];
-                uint32_t& b = v[2 * g * half + j + half];
-                const TwPair t = lane_slot(tw_mirror, G - G0 + (G - 1 - g));
-                const uint32_t s_ = a + b, d = b - a + bound * Q;
-                a = LAZY ? s_ : csub(s_, TWO_Q);
-                b = mul_shoup(d, t);
-            }
-        }
+    // Inverse, cols layout (the first LB2 levels), input in NTT-domain (bit-reversed) order.
+    //  LAZY  : cyclic decimation-in-time with omega^-1 (the structure of the reference's radix2INTT,
+    //          NTT.cu:1473-1494); the twiddle of level s depends only on the position inside the 2^(s+1)
+    //          group, so it is the same for every lane (constant bank), and position 0 needs no multiply.
+    //          `tw` unused.  Input |v| < q.
+    //  Harvey: merged Gentleman-Sande; tw = lane_ptrs().inv (the forward table mirrored: zeta[k]^-1 =
+    //          -zeta[k'], k' the mirror of k in its level).  Input < 2q.
+    static QT_HD void inv_cols(uint32_t (&v)[E], const TwQuad* tw) {
         if (LAZY) {
 #pragma unroll
-            for (uint32_t r = 0; r < E; r++)
-                if (bound_after_cols_inverse(r) > MID) v[r] = fold2q(v[r]);
-        }
-    }
-
-    // rows layout, inverse levels LB1-1..0, output scale K folded into the last level, canonical
-    template <int KIND> static QT_HD void inv_rows(uint32_t (&v)[E]) {
+            for (uint32_t s_ = 0; s_ < LB2; s_++) {
+                const uint32_t l = 1u << s_;
 #pragma unroll
-        for (uint32_t k = 0; k < LB1; k++) {
-            const uint32_t l = LB1 - 1 - k;
-            const uint32_t half = 1u << k;
-            const uint32_t bound = LAZY ? (MID << k) : 2u;
+                for (uint32_t i = 0; i < E / 2; i++) {
+                    const uint32_t u = i / l, j = i % l;
+                    uint32_t& x = v[2 * l * u + j];
+                    uint32_t& y = v[2 * l * u + j + l];
+                    if (j == 0) {
+                        const uint32_t a = x, b = y;
+                        x = a + b;
+                        y = a - b;
+                    } else {
+                        ct(x, y, uni_tw<SET, UNI_INV_PLAIN>(l + j));
+                    }
+                }
+            }
+        } else {
 #pragma unroll
-            for (uint32_t i = 0; i < E / 2; i++) {
-                const uint32_t g = i / half, j = i % half;
-                uint32_t& a = v[2 * g * half + j];
-                uint32_t& b = v[2 * g * half + j + half];
-                const TwPair t = uni_tw<SET, KIND>((1u << l) + g);
-                if (l != 0) {
-                    gs(a, b, t, bound);
-                } else {  // last level: both outputs are multiplied (K resp. K*zeta^-1)
-                    const uint32_t s = a + b, d = a - b + bound * Q;
-                    a = csub(mul_shoup(s, uni_tw<SET, KIND>(0)), Q);
-                    b = csub(mul_shoup(d, t), Q);
+            for (uint32_t k = 0; k < LB2; k++) {
+                const uint32_t half = 1u << k;
+                const uint32_t G = E / (2 * half);
+#pragma unroll
+                for (uint32_t i = 0; i < E / 2; i++) {
+                    const uint32_t g = i / half, j = i % half;
+                    gs(v[2 * g * half + j], v[2 * g * half + j + half], lane_slot(tw, G - G0 + (G - 1 - g), BLOCKS));
                 }
             }
         }
     }
 
-    // NTT-domain product of two forward outputs (each < FWD_BOUND*q): a*b*2^-32 mod q in [0,2q)
-    static QT_HD void pointwise_mont(uint32_t (&a)[E], const uint32_t (&b)[E]) {
+    // Inverse, rows layout (the last LB1 levels) and the output scale; result canonical in [0,q).
+    //  LAZY  : DIT levels with per-lane twiddles (p.inv), then every coefficient i is multiplied by
+    //          n^-1 psi^-i — the reference's invPhi table (NTT.cu:1846-1849) — from p.scale; the FUSED
+    //          scale table also carries the 2^32 of the pointwise Montgomery product.
+    //  Harvey: merged Gentleman-Sande with uniform twiddles, scale folded into the last level.
+    template <int KIND> static QT_HD void inv_rows(uint32_t (&v)[E], const LanePtrs& p) {
+        if (LAZY) {
 #pragma unroll
-        for (uint32_t r = 0; r < E; r++) {
-            if (LAZY) a[r] = mul_mont(a[r], b[r]);
-            else a[r] = mul_mont(csub(a[r], TWO_Q), csub(b[r], TWO_Q));
+            for (uint32_t k = 0; k < LB1; k++) {
+                const uint32_t G = 1u << k;
+#pragma unroll
+                for (uint32_t i = 0; i < E / 2; i++) {
+                    const uint32_t u = i / G, g = i % G;
+                    ct(v[2 * G * u + g], v[2 * G * u + g + G], lane_slot(p.inv, G - 1 + g, LPP));
+                }
+            }
+#pragma unroll
+            for (uint32_t r = 0; r < E; r++) v[r] = scanon(smul_shoup(v[r], lane_slot(p.scale, r, LPP)));
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < LB1; k++) {
+                const uint32_t l = LB1 - 1 - k;
+                const uint32_t half = 1u << k;
+#pragma unroll
+                for (uint32_t i = 0; i < E / 2; i++) {
+                    const uint32_t g = i / half, j = i % half;
+                    uint32_t& a = v[2 * g * half + j];
+                    uint32_t& b = v[2 * g * half + j + half];
+                    const TwPair t = uni_tw<SET, KIND>((1u << l) + g);
+                    if (l != 0) {
+                        const uint32_t s_ = a + b, d = a - b + TWO_Q;
+                        a = csub(s_, TWO_Q);
+                        b = mul_shoup(d, t);
+                    } else {  // last level: both outputs are multiplied (K resp. K*zeta^-1)
+                        const uint32_t s_ = a + b, d = a - b + TWO_Q;
+                        a = csub(mul_shoup(s_, uni_tw<SET, KIND>(0)), Q);
+                        b = csub(mul_shoup(d, t), Q);
+                    }
+                }
+            }
         }
     }
 
+    // NTT-domain product of two forward outputs: a*b*2^-32 mod q (LAZY: signed, |.| < q; Harvey: [0,2q))
+    static QT_HD uint32_t pw(uint32_t a, uint32_t b) {
+        return LAZY ? smul_mont(a, b) : mul_mont(csub(a, TWO_Q), csub(b, TWO_Q));
+    }
+    static QT_HD void pointwise_mont(uint32_t (&a)[E], const uint32_t (&b)[E]) {
+#pragma unroll
+        for (uint32_t r = 0; r < E; r++) a[r] = pw(a[r], b[r]);
+    }
     // same, the second operand read back from a stash written with sts_cols (keeps it out of registers)
     static QT_HD void pointwise_mont_stash(uint32_t (&a)[E], const uint32_t* stash, uint32_t lane) {
 #pragma unroll
         for (uint32_t c = 0; c < E / 4; c++) {
             const U4 u = *reinterpret_cast<const U4*>(stash + swz(E * lane + 4 * c));
-            const uint32_t b[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
-                if (LAZY) a[4 * c + k] = mul_mont(a[4 * c + k], b[k]);
-                else a[4 * c + k] = mul_mont(csub(a[4 * c + k], TWO_Q), csub(b[k], TWO_Q));
-            }
+            a[4 * c] = pw(a[4 * c], u.x);
+            a[4 * c + 1] = pw(a[4 * c + 1], u.y);
+            a[4 * c + 2] = pw(a[4 * c + 2], u.z);
+            a[4 * c + 3] = pw(a[4 * c + 3], u.w);
         }
+    }
+    // forward output times a canonical NTT-domain operand (qt_polymul_ntt)
+    static QT_HD uint32_t pw_canonical(uint32_t a, uint32_t b_canonical) {
+        return LAZY ? smul_mont(a, b_canonical) : mul_mont(csub(a, TWO_Q), b_canonical);
     }
 
     // forward output -> canonical [0,q) (only the unfused forward entry point needs it)
     static QT_HD void canon_fwd(uint32_t (&v)[E]) {
 #pragma unroll
         for (uint32_t r = 0; r < E; r++)
-            v[r] = LAZY ? csub(fold2q(v[r]), Q) : csub(csub(v[r], TWO_Q), Q);
+            v[r] = LAZY ? scanon(smul_shoup(v[r], TwPair{1u, C::MU32})) : csub(csub(v[r], TWO_Q), Q);
     }
 
     // ---- data movement ----------------------------------------------------------------------------

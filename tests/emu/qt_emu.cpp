@@ -26,8 +26,7 @@ template <int SET> struct Emu {
         build_tables(SET, &tab);
         memcpy(h_uni[SET], tab.uni, sizeof(tab.uni));
     }
-    const TwQuad* twf(uint32_t lane) const { return tab.lane_fwd.data() + lane % T::BLOCKS; }
-    const TwQuad* twi(uint32_t lane) const { return tab.lane_fwd.data() + (T::BLOCKS - 1 - lane % T::BLOCKS); }
+    typename T::LanePtrs ptrs(uint32_t lane, int kind) const { return T::lane_ptrs(tab.block[kind].data(), lane); }
 
     void polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
         alignas(16) static uint32_t buf[64 * 32];
@@ -48,18 +47,18 @@ template <int SET> struct Emu {
             for (uint32_t l = 0; l < 32; l++) {
                 T::fwd_rows(vy(l));
                 T::sts_rows(vy(l), buf, l);
-                T::fwd_cols(vx(l), twf(l));
+                T::fwd_cols(vx(l), ptrs(l, 1).fwd);
             }
             for (uint32_t l = 0; l < 32; l++) {
                 T::lds_cols(vy(l), buf, l);
-                T::fwd_cols(vy(l), twf(l));
+                T::fwd_cols(vy(l), ptrs(l, 1).fwd);
                 T::pointwise_mont(vy(l), vx(l));
-                T::inv_cols(vy(l), twi(l));
+                T::inv_cols(vy(l), ptrs(l, 1).inv);
             }
             for (uint32_t l = 0; l < 32; l++) T::sts_cols(vy(l), buf, l);
             for (uint32_t l = 0; l < 32; l++) T::lds_rows(vy(l), buf, l);
             for (uint32_t l = 0; l < 32; l++) {
-                T::template inv_rows<UNI_INV_FUSED>(vy(l));
+                T::template inv_rows<UNI_INV_FUSED>(vy(l), ptrs(l, 1));
                 T::store_rows(vy(l), z + base, l, valid(l));
             }
         }
@@ -80,7 +79,7 @@ template <int SET> struct Emu {
             }
             for (uint32_t l = 0; l < 32; l++) {
                 T::lds_cols(v(l), buf, l);
-                T::fwd_cols(v(l), twf(l));
+                T::fwd_cols(v(l), ptrs(l, 0).fwd);
                 T::canon_fwd(v(l));
             }
             for (uint32_t l = 0; l < 32; l++) T::sts_cols(v(l), buf, l);
@@ -103,12 +102,12 @@ template <int SET> struct Emu {
             }
             for (uint32_t l = 0; l < 32; l++) {
                 T::lds_cols(v(l), buf, l);
-                T::inv_cols(v(l), twi(l));
+                T::inv_cols(v(l), ptrs(l, 0).inv);
             }
             for (uint32_t l = 0; l < 32; l++) T::sts_cols(v(l), buf, l);
             for (uint32_t l = 0; l < 32; l++) T::lds_rows(v(l), buf, l);
             for (uint32_t l = 0; l < 32; l++) {
-                T::template inv_rows<UNI_INV_PLAIN>(v(l));
+                T::template inv_rows<UNI_INV_PLAIN>(v(l), ptrs(l, 0));
                 T::store_rows(v(l), a + base, l, valid(l));
             }
         }

@@ -26,10 +26,36 @@ template <int EXTRA> __device__ __forceinline__ void fwd_rows_padded(uint32_t (&
     }
 }
 
+// probe: signed Cooley-Tukey butterfly with the add folded into the multiply-add:
+//   hi = mulhi.s32(y, ws); u = y*w + x; x' = u - hi*q; y' = 2x - x'      (3 multiply-pipe + 1 ALU instruction)
+template <int EXTRA> __device__ __forceinline__ void fwd_rows_signed(uint32_t (&vu)[T::E], uint32_t (&d)[8]) {
+    int (&v)[T::E] = reinterpret_cast<int (&)[T::E]>(vu);
+    constexpr int Q = (int)T::Q;
+#pragma unroll
+    for (uint32_t l = 0; l < T::LB1; l++) {
+        const uint32_t half = T::E >> (l + 1);
+#pragma unroll
+        for (uint32_t i = 0; i < T::E / 2; i++) {
+            const uint32_t g = i / half, j = i % half;
+            const TwPair t = uni_tw<SET_III, UNI_FWD>((1u << l) + g);
+            int& x = v[2 * g * half + j];
+            int& y = v[2 * g * half + j + half];
+            const int hi = __mulhi(y, (int)t.ws);
+            const int u = y * (int)t.w + x;
+            const int xn = u - hi * Q;
+            y = x + x - xn;
+            x = xn;
+#pragma unroll
+            for (int e = 0; e < EXTRA; e++)
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(d[(i + e) & 7]) : "r"(d[(i + e + 3) & 7]));
+        }
+    }
+}
+
 template <int MODE> __global__ void __launch_bounds__(768, 1) k(uint32_t* out, const TwQuad* g_tw, int iters, long long* cyc) {
     extern __shared__ uint4 sm[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(sm);
-    for (int i = threadIdx.x; i < (int)(T::SLOT_PAIRS * T::BLOCKS); i += blockDim.x) s_tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < (int)T::TABLE_QUADS; i += blockDim.x) s_tw[i] = g_tw[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     uint32_t v[T::E];
@@ -39,13 +65,17 @@ template <int MODE> __global__ void __launch_bounds__(768, 1) k(uint32_t* out, c
     long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
         if (MODE == 0) T::fwd_rows(v);
+        if (MODE == 20) fwd_rows_signed<0>(v, dmy);
+        if (MODE == 21) fwd_rows_signed<1>(v, dmy);
+        if (MODE == 22) fwd_rows_signed<2>(v, dmy);
         if (MODE == 10) fwd_rows_padded<1>(v, dmy);
         if (MODE == 11) fwd_rows_padded<2>(v, dmy);
         if (MODE == 12) fwd_rows_padded<4>(v, dmy);
-        if (MODE == 1) T::fwd_cols(v, s_tw + lane);
-        if (MODE == 2) { T::fwd_rows(v); T::fwd_cols(v, s_tw + lane); }
-        if (MODE == 3) { T::inv_cols(v, s_tw + 31 - lane); T::inv_rows<UNI_INV_FUSED>(v); }
-        if (MODE == 4) { T::fwd_rows(v); T::fwd_cols(v, s_tw + lane); T::inv_cols(v, s_tw + 31 - lane); T::inv_rows<UNI_INV_FUSED>(v); }
+        const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
+        if (MODE == 1) T::fwd_cols(v, P.fwd);
+        if (MODE == 2) { T::fwd_rows(v); T::fwd_cols(v, P.fwd); }
+        if (MODE == 3) { T::inv_cols(v, P.inv); T::inv_rows<UNI_INV_FUSED>(v, P); }
+        if (MODE == 4) { T::fwd_rows(v); T::fwd_cols(v, P.fwd); T::inv_cols(v, P.inv); T::inv_rows<UNI_INV_FUSED>(v, P); }
     }
     long long t1 = clock64();
     uint32_t s = 0;
@@ -57,7 +87,7 @@ template <int MODE> __global__ void __launch_bounds__(768, 1) k(uint32_t* out, c
 
 static int g_threads = 512;
 template <int MODE> void run(const char* name, double bf_per_iter, int sms, uint32_t* out, const TwQuad* tw, long long* cyc) {
-    const int iters = 400, smem = T::SLOT_PAIRS * T::BLOCKS * sizeof(TwQuad);
+    const int iters = 400, smem = T::TABLE_QUADS * sizeof(TwQuad);
     k<MODE><<<sms, g_threads, smem>>>(out, tw, 10, cyc);
     cudaDeviceSynchronize();
     k<MODE><<<sms, g_threads, smem>>>(out, tw, iters, cyc);
@@ -74,8 +104,8 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     HostTables tab; build_tables(SET_III, &tab);
     cudaMemcpyToSymbol(c_uni, tab.uni, sizeof(tab.uni), (size_t)SET_III * sizeof(tab.uni));
-    TwQuad* tw; cudaMalloc(&tw, tab.lane_fwd.size() * sizeof(TwQuad));
-    cudaMemcpy(tw, tab.lane_fwd.data(), tab.lane_fwd.size() * sizeof(TwQuad), cudaMemcpyHostToDevice);
+    TwQuad* tw; cudaMalloc(&tw, tab.block[1].size() * sizeof(TwQuad));
+    cudaMemcpy(tw, tab.block[1].data(), tab.block[1].size() * sizeof(TwQuad), cudaMemcpyHostToDevice);
     uint32_t* out; long long* cyc;
     cudaMalloc(&out, (size_t)p.multiProcessorCount * 768 * 4); cudaMalloc(&cyc, p.multiProcessorCount * 8);
     printf("{\n");
@@ -86,6 +116,9 @@ int main() {
         run<2>(nm, 160, p.multiProcessorCount, out, tw, cyc);
     }
     g_threads = 512;
+    run<20>("signed fwd_rows, add folded into IMAD (3 FMA + 1 ALU)", 80, p.multiProcessorCount, out, tw, cyc);
+    run<21>("signed fwd_rows + 1 extra ALU instr per butterfly", 80, p.multiProcessorCount, out, tw, cyc);
+    run<22>("signed fwd_rows + 2 extra ALU instr per butterfly", 80, p.multiProcessorCount, out, tw, cyc);
     run<10>("fwd_rows + 1 extra ALU instr per butterfly (3 non-FMA per butterfly)", 80, p.multiProcessorCount, out, tw, cyc);
     run<11>("fwd_rows + 2 extra ALU instr per butterfly (4 non-FMA per butterfly)", 80, p.multiProcessorCount, out, tw, cyc);
     run<12>("fwd_rows + 4 extra ALU instr per butterfly (6 non-FMA per butterfly)", 80, p.multiProcessorCount, out, tw, cyc);
