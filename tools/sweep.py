@@ -15,6 +15,8 @@ import torch
 import torch.distributed as dist
 from qtesla_b200_loader import load
 
+_OUT = os.dup(1)   # JSON lines go to the real stdout; library chatter (NCCL banner) to stderr
+os.dup2(2, 1)
 ap = argparse.ArgumentParser()
 ap.add_argument("--set", default="III")
 ap.add_argument("--min-log2", type=int, default=10)
@@ -71,7 +73,7 @@ for lg in range(args.min_log2, args.max_log2 + 1):
         if cpu_rate:
             line["cpu_reference_polymuls_per_s"] = cpu_rate
             line["cpu_threads"] = len(os.sched_getaffinity(0))
-        print(json.dumps(line), flush=True)
+        os.write(_OUT, (json.dumps(line) + "\n").encode())
     del x, y, z
 eng.close()
 if world > 1:
