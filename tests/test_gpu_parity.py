@@ -347,3 +347,22 @@ def test_batch_beyond_32bit_word_index(engines, oracle):
         assert np.array_equal(z[lo * n:(lo + 3) * n].cpu().numpy().view(np.uint32), oracle.polymul(1, xs, ys))
     del x, y, z
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_full_batch_worst_case_operands(engines, s):
+    """Every coefficient q-1 (the largest magnitude the lazy ranges have to absorb), whole bench batch:
+    (q-1)*(q-1) == 1*1, so every product is the all-ones known answer z[k] = 2k+2-n (mod q)."""
+    import torch
+    eng = engines[s]
+    B, n, q = FULL_BATCH[s], eng.n, eng.q
+    x = torch.full((B * n,), q - 1, dtype=torch.int32, device="cuda")
+    z = torch.empty_like(x)
+    eng.polymul(x, x, z)
+    eng.synchronize()
+    exp = torch.from_numpy(((2 * np.arange(n, dtype=np.int64) + 2 - n) % q).astype(np.int32)).cuda()
+    assert torch.equal(z.view(B, n), exp.expand(B, n))
+    # same through the unfused entry points
+    w = x.clone()
+    eng.ntt_forward(w); eng.pointwise(w, w, w); eng.ntt_inverse(w); eng.synchronize()
+    assert torch.equal(w, z)
