@@ -49,9 +49,10 @@ struct qt_ctx {
     size_t smem_fused = 0, smem_one = 0, smem_tma = 0;
     uint64_t launches = 0;
     // host pipeline (qt_polymul_host): lazily created
-    static constexpr int PIPE = 3;
-    cudaStream_t pipe_stream[PIPE] = {nullptr, nullptr, nullptr};
-    uint32_t* pipe_buf[PIPE] = {nullptr, nullptr, nullptr};  // x | y per slot, z overwrites x
+    static constexpr int PIPE = 8;  // maximum number of pipeline slots
+    int pipe_slots = 3;             // slots in use
+    cudaStream_t pipe_stream[PIPE] = {};
+    uint32_t* pipe_buf[PIPE] = {};  // x | y per slot, z overwrites x
     size_t pipe_polys = 0;
     bool pipe_ready = false;
 };
@@ -228,7 +229,11 @@ int ensure_pipe(qt_ctx* c) {
         const size_t w = strtoull(e, nullptr, 10);
         if (w >= c->p.n) c->pipe_polys = w / c->p.n;
     }
-    for (int i = 0; i < qt_ctx::PIPE; i++) {
+    if (const char* e = getenv("QT_PIPE_SLOTS")) {  // tuning aid
+        const int k = atoi(e);
+        if (k >= 1 && k <= qt_ctx::PIPE) c->pipe_slots = k;
+    }
+    for (int i = 0; i < c->pipe_slots; i++) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&c->pipe_buf[i], 2 * c->pipe_polys * c->p.n * sizeof(uint32_t));
         if (e != cudaSuccess) {  // leave no half-built pipeline behind
@@ -461,10 +466,10 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
         }
         if (!rc) rc = (int)cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s);
         done += cnt;
-        slot = (slot + 1) % qt_ctx::PIPE;
+        slot = (slot + 1) % c->pipe_slots;
     }
     // always drain: the caller's buffers must not be touched after we return, error or not
-    for (int i = 0; i < qt_ctx::PIPE; i++) {
+    for (int i = 0; i < c->pipe_slots; i++) {
         const cudaError_t e = cudaStreamSynchronize(c->pipe_stream[i]);
         if (!rc && e != cudaSuccess) rc = (int)e;
     }

@@ -28,6 +28,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     torch.cuda.synchronize(); d2h = 4 * words * 4 / (time.perf_counter() - t0) / 1e9
     print(f"   raw pinned copies: H2D {h2d:.1f} GB/s, D2H {d2h:.1f} GB/s")
 else:
-    for cw in ("1048576", "2097152", "4194304", "8388608", "16777216"):
-        env = dict(os.environ, QT_PIPE_CHUNK_WORDS=cw)
-        subprocess.run([sys.executable, __file__, "child"], env=env)
+    for slots in ("2", "3", "4", "6"):
+        for cw in ("2097152", "4194304", "8388608"):
+            env = dict(os.environ, QT_PIPE_CHUNK_WORDS=cw, QT_PIPE_SLOTS=slots)
+            print("slots", slots, end=" ", flush=True)
+            subprocess.run([sys.executable, __file__, "child"], env=env)
