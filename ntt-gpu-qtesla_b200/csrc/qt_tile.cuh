@@ -8,9 +8,10 @@
 // Design:
 //  * One WARP owns a tile of E*32 consecutive words = PPW whole polynomials (n=512: 2, n=1024: 1,
 //    n=2048: 1 with E=64).  No __syncthreads in the steady state, only __syncwarp.
-//  * Merged-psi Cooley-Tukey forward / Gentleman-Sande inverse: zeta[k] = psi^brv(k).  The forward
-//    output at position i is x(psi^(2 brv(i)+1)) — bit-for-bit what the reference's
-//    Phi-scale + radix2NTTGS (NTT.cu:1866-1876) leaves — with no psi pass and no bit-reverse pass.
+//  * Forward: merged-psi Cooley-Tukey, zeta[k] = psi^brv(k).  The output at position i is
+//    x(psi^(2 brv(i)+1)) — bit-for-bit what the reference's Phi-scale + radix2NTTGS (NTT.cu:1866-1876)
+//    leaves — with no psi pass and no bit-reverse pass.  Inverse: cyclic decimation-in-time + invPhi
+//    scale (small moduli) or merged Gentleman-Sande (29/30-bit moduli); both consume that order.
 //  * Two register-resident passes per transform, joined by one shared-memory transposition:
 //      "rows" layout : register r of lane (p,j) holds coefficient j + LPP*r of polynomial p
 //                      -> the log2(E) levels with the largest strides are thread-local and their
@@ -35,10 +36,8 @@
 
 #if defined(__CUDACC__)
 #define QT_HD __host__ __device__ __forceinline__
-#define QT_CONSTEXPR_HD __host__ __device__ constexpr
 #else
 #define QT_HD inline
-#define QT_CONSTEXPR_HD constexpr
 #endif
 
 namespace qt {
@@ -109,7 +108,6 @@ template <int SET> struct Tile {
     //             (twiddle 1), which may double: |v| < 2^LB2 q, then + 1.5 q per remaining level
     static_assert(!LAZY || (uint64_t)(2 + 3 * LOGN) * Q < (1ull << 32), "forward range");           // 2*(1+1.5 logn) q < 2^32
     static_assert(!LAZY || ((uint64_t)(4u << LB2) + 3 * LB1) * Q < (1ull << 32), "inverse range");  // (2*2^LB2 + 1.5 LB1) q < 2^31
-    static constexpr uint32_t FWD_BOUND = LAZY ? (2 * LOGN + 1) : 4;  // |forward output| < FWD_BOUND*q
 
     // ---- modular arithmetic ---------------------------------------------------------------------
     // y*w mod q for ANY 32-bit y, result in [0,2q)   (Shoup / Harvey), w with floor(w*2^32/q)
