@@ -429,6 +429,8 @@ def main():
             return a0.elapsed_time(a1) / reps
         w.copy_(x)
         for nm, fn, bytes_per_coeff in (("qt_ntt_forward", lambda: e2.ntt_forward(w, batch), 8), ("qt_ntt_inverse", lambda: e2.ntt_inverse(w, batch), 8),
+                                        ("qt_ntt_forward_natural", lambda: e2.ntt_forward_natural(w, batch), 8),
+                                        ("qt_ntt_inverse_natural", lambda: e2.ntt_inverse_natural(w, batch), 8),
                                         ("qt_pointwise", lambda: e2.pointwise(x, y, w, batch), 12), ("qt_bitrev_copy", lambda: e2.bitrev_copy(x, w, batch), 8)):
             t = timed(fn)
             unfused[nm] = {"polys_per_s": batch / (t * 1e-3), "GB_per_s": batch * p.n * bytes_per_coeff / (t * 1e-3) / 1e9,

@@ -104,6 +104,13 @@ int qt_ntt_forward(qt_ctx* ctx, uint32_t* d_a, size_t batch);
 /* inverse NTT in place, NTT domain -> natural, includes n^-1 psi^-i.  Replaces radix2INTT_gpu0/1/2
  * (NTT.cu:1374-1433, driver 2151-2160); result == radix2INTT + invPhi scale (NTT.cu:1845-1849). */
 int qt_ntt_inverse(qt_ctx* ctx, uint32_t* d_a, size_t batch);
+/* The same two transforms with the NTT domain in NATURAL order (position k holds x(psi^(2k+1))) —
+ * the ordering the reference's Stockham pipeline works in: forward == Phi scale + radix2NTTStock
+ * (NTT.cu:1162-1191; GPU NTTStock_gpu0/1/2 1085-1153, driver 2040-2049), inverse == radix2INTTStock
+ * + invPhi scale (NTT.cu:1339-1370; GPU INTTStock_gpu0/1/2 1268-1337, driver 2058-2067).  In place,
+ * one launch, no scratch array; equal to qt_ntt_forward followed by qt_bitrev_copy (resp. preceded). */
+int qt_ntt_forward_natural(qt_ctx* ctx, uint32_t* d_a, size_t batch);
+int qt_ntt_inverse_natural(qt_ctx* ctx, uint32_t* d_a, size_t batch);
 /* c = a*b mod q, element-wise.  Replaces pointwise_mult (NTT.cu:1155-1160). d_c may alias. */
 int qt_pointwise(qt_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, size_t batch);
 /* z = x*y mod (X^n+1, q), fused forward -> pointwise -> inverse in ONE launch; HBM is touched once

@@ -80,6 +80,8 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
     QT_CUDA(cudaFuncSetAttribute(k_polymul<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
     QT_CUDA(cudaFuncSetAttribute(k_ntt_forward<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
     QT_CUDA(cudaFuncSetAttribute(k_ntt_inverse<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
+    QT_CUDA(cudaFuncSetAttribute(k_ntt_natural<SET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
+    QT_CUDA(cudaFuncSetAttribute(k_ntt_natural<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_DIRECT));
     int occ = 0;
     QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polymul<SET>, WARPS_PER_CTA * 32, S::SMEM_DIRECT));
     if (occ < 1) return QT_ERR_UNSUPPORTED;
@@ -186,6 +188,15 @@ template <int SET> int launch_inverse(qt_ctx* c, uint32_t* a, size_t B) {
     if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, true>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_tab[0]);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+template <int SET> int launch_natural(qt_ctx* c, uint32_t* a, size_t B, bool inverse) {
+    const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
+    if (inverse)
+        k_ntt_natural<SET, true><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_tab[0]);
+    else
+        k_ntt_natural<SET, false><<<grid_for(c->grid_fwd, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_tab[0]);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -397,6 +408,18 @@ int qt_ntt_inverse(qt_ctx* c, uint32_t* a, size_t B) {
     if (!B) return 0;
     DeviceGuard g(c->device);
     return QT_DISPATCH(c, launch_inverse, c, a, B);
+}
+int qt_ntt_forward_natural(qt_ctx* c, uint32_t* a, size_t B) {
+    if (!c || (!a && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_natural, c, a, B, false);
+}
+int qt_ntt_inverse_natural(qt_ctx* c, uint32_t* a, size_t B) {
+    if (!c || (!a && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    DeviceGuard g(c->device);
+    return QT_DISPATCH(c, launch_natural, c, a, B, true);
 }
 int qt_pointwise(qt_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t B) {
     if (!c || ((!a || !b || !o) && B)) return QT_ERR_BAD_ARG;

@@ -378,6 +378,51 @@ k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     }
 }
 
+// Natural-order NTT domain (what the reference's Stockham pipeline produces, NTT.cu:2040-2049):
+// forward = natural -> natural, inverse = natural -> natural.  Same arithmetic as above; the
+// bit-reversal is folded into the global access of the cols layout (Tile::nat_off), which saves one
+// shared-memory transposition per transform instead of costing a separate permutation pass.
+template <int SET, bool INVERSE>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_ntt_natural(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
+    using T = Tile<SET>;
+    using S = KernelShape<SET>;
+    extern __shared__ uint4 smem_raw[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
+    const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+    for (size_t tile = (size_t)blockIdx.x * WARPS_PER_CTA + warp; tile < ntiles;
+         tile += (size_t)gridDim.x * WARPS_PER_CTA) {
+        const size_t base = tile * T::C::TILE_WORDS;
+        const bool valid = tile * T::PPW + lane / T::LPP < batch;
+        uint32_t v[T::E];
+        if (!INVERSE) {
+            T::load_rows(v, a + base, lane, valid);
+            T::fwd_rows(v);
+            T::sts_rows(v, buf, lane);
+            __syncwarp();  // also orders every lane's loads before the in-place stores below
+            T::lds_cols(v, buf, lane);
+            T::fwd_cols(v, P.fwd);
+            T::canon_fwd(v);
+            T::store_cols_natural(v, a + base, lane, valid);
+        } else {
+            T::load_cols_natural(v, a + base, lane, valid);
+            T::inv_cols(v, P.inv);
+            T::sts_cols(v, buf, lane);
+            __syncwarp();
+            T::lds_rows(v, buf, lane);
+            T::template inv_rows<UNI_INV_PLAIN>(v, P);
+            T::store_rows(v, a + base, lane, valid);
+        }
+        __syncwarp();  // the buffer is rewritten by the next tile
+    }
+}
+
 // TMA-staged single transform (forward or inverse), in place.  Two one-tile buffers per warp alternate
 // between "staging of the next tile" (bulk copy in flight) and "current tile: staging, then transposition
 // scratch".  Same arithmetic as k_ntt_forward / k_ntt_inverse, which remain the fallback for operands

@@ -325,6 +325,26 @@ template <int SET> struct Tile {
         for (uint32_t r = 0; r < E; r++)
             if (valid) g_tile[row_off(lane, r)] = v[r];
     }
+    // Natural-order view of the NTT domain.  A thread of the cols layout holds the bit-reversed-order
+    // words E*l+r (l = lane within its polynomial); their natural-order positions are
+    // brv(E*l+r) = brv_LOGE(r)*LPP + brv_log2(LPP)(l): for a fixed register the lanes of one polynomial
+    // cover one contiguous LPP-word run, so the accesses stay coalesced without a transposition.
+    static QT_HD uint32_t nat_off(uint32_t lane, uint32_t r) {
+        const uint32_t l = lane % LPP;
+        uint32_t bl = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < C::LOGN - LOGE; b++) bl |= ((l >> b) & 1u) << (C::LOGN - LOGE - 1 - b);
+        return (lane / LPP) * N + c_bitrev(r, LOGE) * LPP + bl;
+    }
+    static QT_HD void load_cols_natural(uint32_t (&v)[E], const uint32_t* g_tile, uint32_t lane, bool valid) {
+#pragma unroll
+        for (uint32_t r = 0; r < E; r++) v[r] = valid ? g_tile[nat_off(lane, r)] : 0u;
+    }
+    static QT_HD void store_cols_natural(const uint32_t (&v)[E], uint32_t* g_tile, uint32_t lane, bool valid) {
+#pragma unroll
+        for (uint32_t r = 0; r < E; r++)
+            if (valid) g_tile[nat_off(lane, r)] = v[r];
+    }
     static QT_HD void sts_rows(const uint32_t (&v)[E], uint32_t* buf, uint32_t lane) {
 #pragma unroll
         for (uint32_t r = 0; r < E; r++) buf[swz(row_off(lane, r))] = v[r];

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "qt_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, _sz]),
     "qt_ntt_forward": (C.c_int, [_vp, _vp, _sz]),
     "qt_ntt_inverse": (C.c_int, [_vp, _vp, _sz]),
+    "qt_ntt_forward_natural": (C.c_int, [_vp, _vp, _sz]),
+    "qt_ntt_inverse_natural": (C.c_int, [_vp, _vp, _sz]),
     "qt_pointwise": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
     "qt_polymul": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
     "qt_bitrev_copy": (C.c_int, [_vp, _vp, _vp, _sz]),
@@ -193,6 +195,12 @@ class Engine:
     def ntt_inverse(self, d_a, batch=None):
         _check(lib().qt_ntt_inverse(self._h, _addr(d_a), self._batch(d_a, batch)))
 
+    def ntt_forward_natural(self, d_a, batch=None):
+        _check(lib().qt_ntt_forward_natural(self._h, _addr(d_a), self._batch(d_a, batch)))
+
+    def ntt_inverse_natural(self, d_a, batch=None):
+        _check(lib().qt_ntt_inverse_natural(self._h, _addr(d_a), self._batch(d_a, batch)))
+
     def pointwise(self, d_a, d_b, d_c, batch=None):
         _check(lib().qt_pointwise(self._h, _addr(d_a), _addr(d_b), _addr(d_c), self._batch(d_a, batch)))
 
@@ -243,6 +251,12 @@ class Engine:
 
     def inverse_np(self, a):
         return self._roundtrip(lambda t: (self.ntt_inverse(t), t)[1], a)
+
+    def forward_natural_np(self, a):
+        return self._roundtrip(lambda t: (self.ntt_forward_natural(t), t)[1], a)
+
+    def inverse_natural_np(self, a):
+        return self._roundtrip(lambda t: (self.ntt_inverse_natural(t), t)[1], a)
 
     def polymul_np(self, x, y):
         import torch

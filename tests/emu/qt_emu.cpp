@@ -113,6 +113,49 @@ template <int SET> struct Emu {
         }
     }
 
+    // natural-order NTT domain (k_ntt_natural): the permutation lives in the global access pattern
+    void forward_natural(uint32_t* a, size_t batch) {
+        alignas(16) static uint32_t buf[64 * 32];
+        const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+        std::vector<uint32_t> V(32 * E);
+        auto v = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&V[lane * E]); };
+        for (size_t tile = 0; tile < ntiles; tile++) {
+            const size_t base = tile * T::C::TILE_WORDS;
+            auto valid = [&](uint32_t lane) { return tile * T::PPW + lane / T::LPP < batch; };
+            for (uint32_t l = 0; l < 32; l++) {
+                T::load_rows(v(l), a + base, l, valid(l));
+                T::fwd_rows(v(l));
+                T::sts_rows(v(l), buf, l);
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                T::lds_cols(v(l), buf, l);
+                T::fwd_cols(v(l), ptrs(l, 0).fwd);
+                T::canon_fwd(v(l));
+                T::store_cols_natural(v(l), a + base, l, valid(l));
+            }
+        }
+    }
+    void inverse_natural(uint32_t* a, size_t batch) {
+        alignas(16) static uint32_t buf[64 * 32];
+        const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+        std::vector<uint32_t> V(32 * E);
+        auto v = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&V[lane * E]); };
+        for (size_t tile = 0; tile < ntiles; tile++) {
+            const size_t base = tile * T::C::TILE_WORDS;
+            auto valid = [&](uint32_t lane) { return tile * T::PPW + lane / T::LPP < batch; };
+            for (uint32_t l = 0; l < 32; l++) {
+                T::load_cols_natural(v(l), a + base, l, valid(l));
+                T::inv_cols(v(l), ptrs(l, 0).inv);
+                T::sts_cols(v(l), buf, l);
+            }
+            for (uint32_t l = 0; l < 32; l++) T::lds_rows(v(l), buf, l);
+            for (uint32_t l = 0; l < 32; l++) {
+                T::template inv_rows<UNI_INV_PLAIN>(v(l), ptrs(l, 0));
+                T::store_rows(v(l), a + base, l, valid(l));
+            }
+        }
+    }
+
     // worst bank-conflict degree of the four shared-memory access patterns
     // (32-bit: 32 lanes per wavefront; 128-bit: 8 lanes per wavefront, 4 banks each)
     int bank_conflicts() {
@@ -224,6 +267,14 @@ int qtemu_forward(int set, uint32_t* a, size_t batch) {
 }
 int qtemu_inverse(int set, uint32_t* a, size_t batch) {
     EMU_DISPATCH(set, inverse(a, batch));
+    return 0;
+}
+int qtemu_forward_natural(int set, uint32_t* a, size_t batch) {
+    EMU_DISPATCH(set, forward_natural(a, batch));
+    return 0;
+}
+int qtemu_inverse_natural(int set, uint32_t* a, size_t batch) {
+    EMU_DISPATCH(set, inverse_natural(a, batch));
     return 0;
 }
 int qtemu_nussbaumer(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring) {

@@ -23,6 +23,8 @@ def emu():
     L.qtemu_polymul.argtypes = [C.c_int, u, u, u, C.c_size_t]
     L.qtemu_forward.argtypes = [C.c_int, u, C.c_size_t]
     L.qtemu_inverse.argtypes = [C.c_int, u, C.c_size_t]
+    L.qtemu_forward_natural.argtypes = [C.c_int, u, C.c_size_t]
+    L.qtemu_inverse_natural.argtypes = [C.c_int, u, C.c_size_t]
     L.qtemu_nussbaumer.argtypes = [C.c_int, u, u, u, C.c_size_t, C.c_int]
     return L
 
@@ -46,6 +48,24 @@ def test_emulated_kernel_equals_oracle(emu, oracle, s):
     g = f.copy()
     emu.qtemu_inverse(s, _p(g), B)
     assert np.array_equal(g, x)
+
+
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_emulated_natural_order_transforms(emu, oracle, s):
+    """Natural-order NTT domain (the reference's Stockham ordering, NTT.cu:1162-1191, 1339-1370)."""
+    p = oracle.params(s)
+    B = 3
+    rng = np.random.default_rng(40 + s)
+    x = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    x[: p.n] = p.q - 1
+    f = x.copy()
+    assert emu.qtemu_forward_natural(s, _p(f), B) == 0
+    assert np.array_equal(f, oracle.forward_natural(s, x))
+    assert np.array_equal(f, oracle.bitrev_copy(s, oracle.forward(s, x)))
+    g = f.copy()
+    assert emu.qtemu_inverse_natural(s, _p(g), B) == 0
+    assert np.array_equal(g, x)
+    assert np.array_equal(oracle.inverse_natural(s, f), x)
 
 
 @pytest.mark.parametrize("s", ALL_SETS)

@@ -140,6 +140,24 @@ def test_bitrev_copy_and_natural_order(engines, oracle, s):
     assert np.array_equal(nat, oracle.bitrev_copy(s, f))
 
 
+@pytest.mark.parametrize("B", [1, 3, 257, 4099])
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_natural_order_transforms_equal_stockham_oracle(engines, oracle, s, B):
+    """qt_ntt_forward_natural / qt_ntt_inverse_natural == the reference's Stockham pipeline ordering
+    (Phi scale + radix2NTTStock, radix2INTTStock + invPhi scale; NTT.cu:1162-1191, 1339-1370)."""
+    eng = engines[s]
+    x, y = rand_pair(eng.q, B * eng.n, 7000 + 10 * s + B)
+    x[: eng.n] = eng.q - 1
+    f = eng.forward_natural_np(x)
+    assert np.array_equal(f, oracle.forward_natural(s, x))
+    assert np.array_equal(eng.inverse_natural_np(f), x)
+    assert np.array_equal(eng.inverse_natural_np(y), oracle.inverse_natural(s, y))
+    # natural-order pipeline (Stockham variant of the reference) == fused product
+    fy = eng.forward_natural_np(y)
+    z = eng.inverse_natural_np(eng.pointwise_np(f, fy))
+    assert np.array_equal(z, oracle.polymul(s, x, y, 3))  # variant 3 = the Stockham composition
+
+
 def test_in_place_and_fill_uniform(engines, oracle):
     import torch
     eng = engines[1]
