@@ -250,7 +250,7 @@ def main():
     ap.add_argument("--set", default="III", choices=list(SETS))
     ap.add_argument("--batch", type=int, default=0, help="polynomials per GPU per step (default: BASELINE config)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other parameter sets / CPU baseline")
-    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3],
                     help="fused-kernel data path: 0 automatic, 1 direct coalesced loads, 2 TMA-staged")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -395,7 +395,7 @@ def main():
             e2.close()
         st = max(3, min(args.steps, 50))
         variants = {}
-        for vname, v in (("direct_loads", 1), ("tma_staged", 2)):
+        for vname, v in (("direct_loads", 1), ("tma_staged", 2), ("split_tile_n2048", 3)):
             try:
                 e2, _, ms2, _ = run_config(set_id, batch, st, 3, variant=v)
                 variants[vname] = batch * st / (ms2 * 1e-3)
@@ -458,7 +458,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                          "frac": hbm_achieved / float(peaks["hbm_gbs"]), "traffic": traffic,
-                         "peak_source": peaks_src, "kernel": "k_polymul_tma" if eng.kernel_info()["block"] != 256 else "k_polymul",
+                         "peak_source": peaks_src, "kernel": ("k_polymul" if eng.kernel_info()["block"] == 256 else
+                                                                  "k_polymul_split" if (p.n == 2048 and args.variant in (0, 3)) else "k_polymul_tma"),
                          "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_pp * batch,
                          "binding": "int_mul_pipe", "binding_frac": int_achieved / int_peak,

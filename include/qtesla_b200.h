@@ -86,7 +86,8 @@ int qt_destroy(qt_ctx* ctx);
 int qt_set_stream(qt_ctx* ctx, void* cuda_stream);
 int qt_synchronize(qt_ctx* ctx);
 /* fused-kernel data path: 0 = automatic, 1 = direct coalesced loads, 2 = TMA bulk copies staged
- * through shared memory with an mbarrier (needs 16-byte aligned operands) */
+ * through shared memory with an mbarrier (needs 16-byte aligned operands), 3 = n=2048 only: TMA-staged
+ * with the polynomial processed as two 1024-point halves (what "automatic" picks for qTESLA-p-III) */
 int qt_set_fused_variant(qt_ctx* ctx, int variant);
 int qt_device_malloc(qt_ctx* ctx, size_t bytes, void** out_dev);
 int qt_device_free(qt_ctx* ctx, void* dev);

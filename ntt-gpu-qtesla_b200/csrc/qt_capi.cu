@@ -20,7 +20,7 @@
 #include "qt_nussbaumer.cuh"
 
 namespace qt {
-TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX];
+TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
 }
 
 using namespace qt;
@@ -45,7 +45,9 @@ struct qt_ctx {
     int num_sms = 0;
     int grid_fused = 0, grid_fwd = 0, grid_inv = 0, grid_nuss = 0, grid_tma = 0;
     int occ_fused = 0, occ_tma = 0, tma_warps = 0;
-    int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged
+    TwQuad* d_tab_split = nullptr;          // n=2048 only: tables of the split tile (k_polymul_split)
+    bool split_ok = false;
+    int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged, 3 split tile (n=2048)
     size_t smem_fused = 0, smem_one = 0, smem_tma = 0;
     uint64_t launches = 0;
     // host pipeline (qt_polymul_host): lazily created
@@ -71,7 +73,7 @@ struct DeviceGuard {
 };
 
 std::mutex g_uni_mutex;
-bool g_uni_uploaded[64][NUM_SETS];  // per device
+bool g_uni_uploaded[64][NUM_TILE_SETS];  // per device
 
 template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
     using S = KernelShape<SET>;
@@ -101,7 +103,7 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
     (void)cudaFuncSetAttribute(k_ntt_tma<SET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
     (void)cudaFuncSetAttribute(k_ntt_tma<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
     (void)cudaFuncSetAttribute(k_bitrev_copy<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BitrevShape<SET>::SMEM);
-    (void)cudaFuncSetAttribute(k_polymul_ntt<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
+    (void)cudaFuncSetAttribute(k_polymul_ntt<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM_BCAST);
     (void)cudaFuncSetAttribute(k_polymul_ntt<SET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
     (void)cudaGetLastError();
     QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ntt_forward<SET>, WARPS_PER_CTA * 32, S::SMEM_DIRECT));
@@ -132,6 +134,29 @@ int upload_tables(qt_ctx* c) {
             QT_CUDA(cudaMemcpyToSymbol(c_uni, T.uni, sizeof(T.uni), (size_t)c->set * sizeof(T.uni)));
         }
     }
+    if (c->set == SET_P_III) {  // the split tile of the fused n=2048 kernel
+        HostTables H;
+        build_tables_split(&H);
+        const size_t bytes = H.block[1].size() * sizeof(TwQuad);
+        QT_CUDA(cudaMalloc(&c->d_tab_split, bytes));
+        QT_CUDA(cudaMemcpy(c->d_tab_split, H.block[1].data(), bytes, cudaMemcpyHostToDevice));
+        {
+            std::lock_guard<std::mutex> lk(g_uni_mutex);
+            memcpy(h_uni[SET_P_III_H], H.uni, sizeof(H.uni));
+            if (c->device >= 64 || !g_uni_uploaded[c->device][SET_P_III_H]) {
+                QT_CUDA(cudaMemcpyToSymbol(c_uni, H.uni, sizeof(H.uni), (size_t)SET_P_III_H * sizeof(H.uni)));
+                if (c->device < 64) g_uni_uploaded[c->device][SET_P_III_H] = true;
+            }
+        }
+        int occ = 0;
+        if (cudaFuncSetAttribute(k_polymul_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM) == cudaSuccess &&
+            cudaFuncSetAttribute(k_polymul_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM_BCAST) == cudaSuccess &&
+            cudaFuncSetAttribute(k_polymul_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polymul_split<0>, SplitShape::WARPS * 32, SplitShape::SMEM) == cudaSuccess)
+            c->split_ok = occ > 0;
+        else
+            (void)cudaGetLastError();
+    }
     switch (c->set) {
     case SET_I: return setup_set<SET_I>(c, T);
     case SET_III: return setup_set<SET_III>(c, T);
@@ -150,7 +175,10 @@ template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;  // bulk copies need 16-byte alignment
     const bool tma = c->occ_tma > 0 && aligned && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
-    if (tma)
+    if (SET == SET_P_III && c->split_ok && aligned && (c->variant == 3 || c->variant == 0))
+        k_polymul_split<0><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (B + SplitShape::WARPS - 1) / SplitShape::WARPS)),
+                          SplitShape::WARPS * 32, SplitShape::SMEM, s>>>(x, y, z, B, c->d_tab_split);
+    else if (tma)
         k_polymul_tma<SET><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS)),
                              TmaCfg<SET>::WARPS * 32, c->smem_tma, s>>>(
             x, y, z, B, c->d_tab[1]);
@@ -164,8 +192,15 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     if (c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
     if ((((uintptr_t)ahat | (uintptr_t)y) & 15) != 0) return QT_ERR_BAD_ARG;  // 128-bit / bulk-copy alignment
+    if (SET == SET_P_III && c->split_ok && c->variant != 2) {
+        const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (B + SplitShape::WARPS - 1) / SplitShape::WARPS));
+        if (bcast) k_polymul_split<1><<<g, SplitShape::WARPS * 32, SplitShape::SMEM_BCAST, c->stream>>>(ahat, y, z, B, c->d_tab_split);
+        else k_polymul_split<2><<<g, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream>>>(ahat, y, z, B, c->d_tab_split);
+        c->launches++;
+        return (int)cudaGetLastError();
+    }
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS));
-    if (bcast) k_polymul_ntt<SET, true><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
+    if (bcast) k_polymul_ntt<SET, true><<<grid, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM_BCAST, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
     else k_polymul_ntt<SET, false><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
     c->launches++;
     return (int)cudaGetLastError();
@@ -338,6 +373,7 @@ int qt_destroy(qt_ctx* c) {
     release_pipe(c);
     for (int k = 0; k < 2; k++)
         if (c->d_tab[k]) cudaFree(c->d_tab[k]);
+    if (c->d_tab_split) cudaFree(c->d_tab_split);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -350,8 +386,9 @@ int qt_set_stream(qt_ctx* c, void* s) {
 }
 
 int qt_set_fused_variant(qt_ctx* c, int variant) {
-    if (!c || variant < 0 || variant > 2) return QT_ERR_BAD_ARG;
+    if (!c || variant < 0 || variant > 3) return QT_ERR_BAD_ARG;
     if (variant == 2 && c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
+    if (variant == 3 && !c->split_ok) return QT_ERR_UNSUPPORTED;
     c->variant = variant;
     return 0;
 }
@@ -556,6 +593,14 @@ int qt_launch_count(qt_ctx* c, uint64_t* out) {
 
 int qt_kernel_info(qt_ctx* c, int* grid, int* block, int* smem, int* per_sm, int* sms) {
     if (!c) return QT_ERR_BAD_ARG;
+    if (c->split_ok && (c->variant == 3 || c->variant == 0)) {
+        if (grid) *grid = c->num_sms;
+        if (block) *block = SplitShape::WARPS * 32;
+        if (smem) *smem = (int)SplitShape::SMEM;
+        if (per_sm) *per_sm = 1;
+        if (sms) *sms = c->num_sms;
+        return 0;
+    }
     const bool tma = c->occ_tma > 0 && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
     if (grid) *grid = tma ? c->grid_tma : c->grid_fused;
     if (block) *block = (tma ? c->tma_warps : WARPS_PER_CTA) * 32;

@@ -135,6 +135,7 @@ template <int SET> struct StageShape {
     static constexpr uint32_t WORDS = T::PPW * POLY_STRIDE;  // one buffer (>= TILE_WORDS)
     static constexpr size_t SMEM = KernelShape<SET>::TW_BYTES + (size_t)TmaCfg<SET>::WARPS * 2 * WORDS * sizeof(uint32_t) +
                                    (size_t)TmaCfg<SET>::WARPS * 2 * sizeof(uint64_t);
+    static constexpr size_t SMEM_BCAST = SMEM + T::N * sizeof(uint32_t);  // + the broadcast a_hat of k_polymul_ntt
     static __device__ __forceinline__ uint32_t off(uint32_t lane, uint32_t r) {
         return (lane / T::LPP) * POLY_STRIDE + (lane % T::LPP) + T::LPP * r;
     }
@@ -226,6 +227,160 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
     }
 }
 
+// Fused product for n = 2048 (qTESLA-p-III) on the SPLIT tile: a polynomial is two 1024-point halves
+// joined by one level, and every transform runs the 32-coefficients-per-thread half code twice (a rolled
+// loop) instead of one 64-coefficients-per-thread pass.  Why: the 64-wide kernel is 7360 instructions
+// (118 KB) of straight-line code, at the edge of the instruction cache — ncu shows 0.5 "no instruction"
+// stall per issue against 0.02 for the n=1024 kernels (profiles/ncu_fused_p3_r01n.json, tools/icache.cu) —
+// and needs 167 registers.  Same buffers as k_polymul_tma: A = x staging -> scratch / stash of the second
+// half -> NTT(x) -> next x;  B = y staging -> scratch / stashes -> next y.  Each 1024-word half of a buffer
+// is used with the half tile's own (swizzled) rows/cols patterns.
+#ifndef QT_SPLIT_WARPS
+#define QT_SPLIT_WARPS 12
+#endif
+struct SplitShape {
+    using T = Tile<SET_P_III_H>;
+    static constexpr int WARPS = QT_SPLIT_WARPS;
+    static constexpr uint32_t HALF = T::N, WORDS = 2 * T::N;          // one buffer = one polynomial
+    static constexpr size_t TW_BYTES = (size_t)T::TABLE_QUADS * sizeof(TwQuad);
+    static constexpr size_t STAGE_BYTES = (size_t)WARPS * 2 * WORDS * sizeof(uint32_t);
+    static constexpr size_t BAR_BYTES = (size_t)WARPS * 2 * sizeof(uint64_t);
+    static constexpr size_t SMEM = TW_BYTES + STAGE_BYTES + BAR_BYTES;
+    static constexpr size_t SMEM_BCAST = SMEM + WORDS * sizeof(uint32_t);  // + the broadcast a_hat (MODE 1)
+};
+
+// MODE 0: z = x*y (x in the first argument).  MODE 1 / 2: the first argument is NTT(a) as qt_ntt_forward
+// leaves it (qt_polymul_ntt): 1 = one a_hat for the whole batch, kept in shared memory; 2 = one per product.
+template <int MODE>
+__global__ void __launch_bounds__(SplitShape::WARPS * 32, 1)
+k_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwQuad* __restrict__ g_lane) {
+    using T = SplitShape::T;
+    using G = SplitShape;
+    extern __shared__ uint4 smem_raw[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
+    constexpr int NW = G::WARPS;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* A = s_stage + warp * 2 * G::WORDS;
+    uint32_t* B = A + G::WORDS;
+    uint64_t* bar_a = s_bar + 2 * warp;
+    uint64_t* bar_b = bar_a + 1;
+    const size_t stride = (size_t)gridDim.x * NW;
+    size_t tile = (size_t)blockIdx.x * NW + warp;  // one polynomial per tile
+    auto issue = [&](const uint32_t* g, uint32_t* st, uint64_t* bar, size_t t) {  // one lane
+        mbar_expect_tx(bar, G::WORDS * (uint32_t)sizeof(uint32_t));
+        bulk_g2s(st, g + t * G::WORDS, G::WORDS * (uint32_t)sizeof(uint32_t), bar);
+    };
+    if (lane == 0) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        if (tile < batch) {
+            if (MODE == 0) issue(x, A, bar_a, tile);
+            issue(y, B, bar_b, tile);
+        }
+    }
+    copy_table_to_smem(s_tw, g_lane, T::TABLE_QUADS);
+    // MODE 1: the one a_hat stays in shared memory (behind the barriers), each half in the half tile's
+    // swizzled cols layout
+    uint32_t* s_ahat = reinterpret_cast<uint32_t*>(s_bar + 2 * NW);
+    if (MODE == 1) {
+        for (uint32_t i = threadIdx.x; i < G::WORDS / 4; i += blockDim.x)
+            *reinterpret_cast<uint4*>(s_ahat + (4 * i / G::HALF) * G::HALF + T::swz(4 * i % G::HALF)) =
+                __ldg(reinterpret_cast<const uint4*>(x) + i);
+    }
+    __syncthreads();
+
+    uint32_t phase = 0;
+    for (uint32_t k = 0; tile < batch; tile += stride, phase ^= 1, k++) {
+        const bool more = tile + stride < batch;
+        // y staging.  MODE 0: always B (x's transform hides the copy).  MODE 1/2: no x, so the two buffers
+        // alternate and the next y is requested a whole tile ahead.
+        uint32_t* ybuf = (MODE == 0 || !(k & 1)) ? B : A;
+        uint64_t* ybar = (MODE == 0 || !(k & 1)) ? bar_b : bar_a;
+        const uint32_t yphase = (MODE == 0) ? phase : ((k >> 1) & 1);
+        if (MODE != 0 && more && lane == 0)  // (the other buffer was released at the end of the previous tile)
+            issue(y, (k & 1) ? B : A, (k & 1) ? bar_b : bar_a, tile + stride);
+        const uint32_t* ah = x + tile * G::WORDS + T::E * lane;  // MODE 2: this lane's line of each half
+        if (MODE == 2) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ah));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ah + G::HALF));
+        }
+        uint32_t v[T::E];
+#pragma unroll 1
+        for (int op = (MODE == 0 ? 0 : 1); op < 2; op++) {  // x, then y (which continues into the inverse)
+            uint32_t* st = op ? ybuf : A;
+            mbar_wait(op ? ybar : bar_a, op ? yphase : phase);
+            {
+                uint32_t hi[T::E];
+#pragma unroll
+                for (uint32_t r = 0; r < T::E; r++) {
+                    v[r] = st[lane + 32 * r];
+                    hi[r] = st[G::HALF + lane + 32 * r];
+                }
+                __syncwarp();  // the staging buffer becomes scratch
+                T::split_fwd(v, hi);
+                T::sts_rows(hi, st + G::HALF, lane);  // parked; read back by the same lane
+            }
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; h++) {
+                uint32_t* sh = st + h * G::HALF;
+                if (h) T::lds_rows(v, sh, lane);
+                T::fwd_rows(v, 32 * h);
+                T::sts_rows(v, sh, lane);
+                __syncwarp();
+                T::lds_cols(v, sh, lane);
+                T::fwd_cols(v, s_tw + h * T::TW_QUADS + lane);
+                if (MODE == 0 && op == 0) {
+                    __syncwarp();                // every lane has read its columns
+                    T::sts_cols(v, sh, lane);    // NTT(x) half h; each lane reads back only what it wrote
+                    continue;
+                }
+                if (MODE == 0) {
+                    T::pointwise_mont_stash(v, A + h * G::HALF, lane);
+                    if (h) {                     // A is free: fetch the next x
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (more && lane == 0) issue(x, A, bar_a, tile + stride);
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t c = 0; c < T::E / 4; c++) {
+                        const uint4 u = (MODE == 1)
+                            ? *reinterpret_cast<const uint4*>(s_ahat + h * G::HALF + T::swz(T::E * lane + 4 * c))
+                            : __ldg(reinterpret_cast<const uint4*>(ah + h * G::HALF) + c);
+                        v[4 * c] = T::pw_canonical(v[4 * c], u.x);
+                        v[4 * c + 1] = T::pw_canonical(v[4 * c + 1], u.y);
+                        v[4 * c + 2] = T::pw_canonical(v[4 * c + 2], u.z);
+                        v[4 * c + 3] = T::pw_canonical(v[4 * c + 3], u.w);
+                    }
+                }
+                T::inv_cols(v, s_tw + (1 - h) * T::TW_QUADS + (T::BLOCKS - 1 - lane));  // mirrored table of the OTHER half
+                __syncwarp();
+                T::sts_cols(v, sh, lane);
+                __syncwarp();
+                T::lds_rows(v, sh, lane);
+                T::template inv_rows<UNI_INV_FUSED>(v, typename T::LanePtrs{nullptr, nullptr, nullptr}, 32 * h);
+                if (h == 0) T::sts_rows(v, sh, lane);  // parked in this lane's own slots until half 1 is done
+            }
+        }
+        // join the halves: last inverse level + scale, canonical
+        uint32_t* zt = z + tile * G::WORDS;
+#pragma unroll
+        for (uint32_t r = 0; r < T::E; r++) {
+            uint32_t a = ybuf[T::swz(T::row_off(lane, r))];
+            T::template split_inv<UNI_INV_FUSED>(a, v[r]);
+            zt[lane + 32 * r] = a;
+            zt[G::HALF + lane + 32 * r] = v[r];
+        }
+        fence_proxy_async();
+        __syncwarp();  // the y buffer is free
+        if (MODE == 0 && more && lane == 0) issue(y, B, bar_b, tile + stride);
+    }
+}
+
 // z = a*y with NTT(a) supplied by the caller (qTESLA's own use: one public polynomial a, transformed
 // once, multiplied by many secrets / sparse challenges).  Two transforms instead of three.
 // a_hat is in the NTT domain exactly as qt_ntt_forward leaves it (canonical, bit-reversed order);
@@ -243,41 +398,48 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
     constexpr int NW = TmaCfg<SET>::WARPS;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // One y buffer per warp, refilled as soon as the inverse has left it (measured: requesting the next y a
+    // whole tile ahead into a second buffer is not faster for these sets, and slower for n=512)
     uint32_t* B = s_stage + warp * 2 * G::WORDS;
-    uint64_t* bar_b = s_bar + 2 * warp;
+    uint64_t* bar0 = s_bar + 2 * warp;
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     const size_t stride = (size_t)gridDim.x * NW;
     size_t tile = (size_t)blockIdx.x * NW + warp;
-    auto issue = [&](size_t t) {
+    auto issue = [&](uint32_t* st, uint64_t* bar, size_t t) {
         const size_t p0 = t * T::PPW;
         const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);
-        mbar_expect_tx(bar_b, np * T::N * (uint32_t)sizeof(uint32_t));
+        mbar_expect_tx(bar, np * T::N * (uint32_t)sizeof(uint32_t));
         if (G::PAD == 0) {
-            bulk_g2s(B, y + p0 * T::N, np * T::N * (uint32_t)sizeof(uint32_t), bar_b);
+            bulk_g2s(st, y + p0 * T::N, np * T::N * (uint32_t)sizeof(uint32_t), bar);
         } else {
             for (uint32_t p = 0; p < np; p++)
-                bulk_g2s(B + p * G::POLY_STRIDE, y + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar_b);
+                bulk_g2s(st + p * G::POLY_STRIDE, y + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar);
         }
     };
     if (lane == 0) {
-        mbar_init(bar_b, 1);
+        mbar_init(bar0, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        if (tile < ntiles) issue(tile);
+        if (tile < ntiles) issue(B, bar0, tile);
     }
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    // BCAST: the one a_hat lives in shared memory for the whole kernel (behind the barriers), stored with
+    // the tile's swizzle so that the 128-bit reads below are conflict-free
+    uint32_t* s_ahat = reinterpret_cast<uint32_t*>(s_bar + 2 * NW);
+    if (BCAST) {
+        for (uint32_t i = threadIdx.x; i < T::N / 4; i += blockDim.x)
+            *reinterpret_cast<uint4*>(s_ahat + T::swz(4 * i)) = __ldg(reinterpret_cast<const uint4*>(a_hat) + i);
+    }
     __syncthreads();
     const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
-    uint32_t phase = 0;
-    for (; tile < ntiles; tile += stride, phase ^= 1) {
+    for (uint32_t k = 0; tile < ntiles; tile += stride, k++) {
         const size_t base = tile * T::C::TILE_WORDS;
         const bool valid = tile * T::PPW + lane / T::LPP < batch;
-        const bool more = tile + stride < ntiles;
         // this lane's E words of a_hat in the cols layout (clamped for the missing polynomial of a tail tile)
-        const uint4* ah = reinterpret_cast<const uint4*>(
-            a_hat + (BCAST ? (size_t)T::E * (lane % T::BLOCKS) : (valid ? base + (size_t)T::E * lane : 0)));
+        const uint4* ah = reinterpret_cast<const uint4*>(a_hat + (valid ? base + (size_t)T::E * lane : 0));
+        if (!BCAST) asm volatile("prefetch.global.L2 [%0];" ::"l"(ah));  // this lane's 128-byte line, needed after the forward transform
         uint32_t v[T::E];
-        mbar_wait(bar_b, phase);
+        mbar_wait(bar0, k & 1);
 #pragma unroll
         for (uint32_t r = 0; r < T::E; r++) v[r] = B[G::off(lane, r)];
         __syncwarp();
@@ -288,11 +450,12 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
         T::fwd_cols(v, P.fwd);
 #pragma unroll
         for (uint32_t c = 0; c < T::E / 4; c++) {
-            const uint4 u = __ldg(ah + c);
+            const uint4 u = BCAST ? *reinterpret_cast<const uint4*>(s_ahat + T::swz(T::E * (lane % T::BLOCKS) + 4 * c))
+                                  : __ldg(ah + c);
             const uint32_t b[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++)
-                v[4 * c + k] = T::pw_canonical(v[4 * c + k], b[k]);
+            for (uint32_t k2 = 0; k2 < 4; k2++)
+                v[4 * c + k2] = T::pw_canonical(v[4 * c + k2], b[k2]);
         }
         T::inv_cols(v, P.inv);
         __syncwarp();
@@ -300,8 +463,8 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
         __syncwarp();
         T::lds_rows(v, B, lane);
         fence_proxy_async();
-        __syncwarp();
-        if (more && lane == 0) issue(tile + stride);
+        __syncwarp();  // B is free: fetch the next tile's y into it
+        if (tile + stride < ntiles && lane == 0) issue(B, bar0, tile + stride);
         T::template inv_rows<UNI_INV_FUSED>(v, P);
         T::store_rows(v, z + base, lane, valid);
     }

@@ -16,6 +16,11 @@
 namespace qt {
 
 enum : int { SET_I = 0, SET_III = 1, SET_P_I = 2, SET_P_III = 3, NUM_SETS = 4 };
+// Internal tile configuration (not a parameter set of the API): qTESLA-p-III seen as TWO 1024-point
+// sub-transforms joined by one split level (X^2048+1 = (X^1024 - zeta)(X^1024 + zeta)).  The fused
+// n=2048 kernel runs the 32-coefficients-per-thread tile code twice per transform instead of a
+// 64-coefficients-per-thread tile (qt_kernels.cuh: k_polymul_split).
+enum : int { SET_P_III_H = 4, NUM_TILE_SETS = 5 };
 
 QT_CHD uint32_t c_mulmod(uint32_t a, uint32_t b, uint32_t q) {
     return (uint32_t)((uint64_t)a * b % q);
@@ -70,6 +75,11 @@ template <> struct Params<SET_P_III> {
     static constexpr uint32_t PSI = c_find_psi(N, Q);
 };
 
+template <> struct Params<SET_P_III_H> {
+    static constexpr uint32_t N = 1024, Q = Params<SET_P_III>::Q;                  // one half of n = 2048
+    static constexpr uint32_t PSI = c_mulmod(Params<SET_P_III>::PSI, Params<SET_P_III>::PSI, Q);
+};
+
 // Everything the kernels need, derived from (N, Q, PSI).
 template <int SET> struct Cfg {
     using P = Params<SET>;
@@ -84,6 +94,10 @@ template <int SET> struct Cfg {
     // Moduli below 2^25 leave >= 7 spare bits in a 32-bit word: butterflies run without any
     // per-level correction ("lazy").  The 29/30-bit moduli use Harvey's [0,4q) butterflies.
     static constexpr bool LAZY = QBITS <= 24;
+    // SPLIT: this tile is one half of a polynomial twice its size; the level joining the halves
+    // (and the output scale) is applied by the caller (Tile::split_fwd / split_inv)
+    static constexpr bool SPLIT = (SET == SET_P_III_H);
+    static constexpr uint32_t HALVES = SPLIT ? 2 : 1;
 
     // warp tile: one warp owns E*32 consecutive words = PPW whole polynomials
     static constexpr uint32_t E = (N == 2048) ? 64 : 32;  // coefficients per thread

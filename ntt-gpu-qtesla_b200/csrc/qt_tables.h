@@ -132,4 +132,56 @@ inline void build_tables(int set, HostTables* T) {
     }
 }
 
+// Tables of the split tile (SET_P_III_H): the n=2048 zeta table cut into the two 1024-point halves.
+// Half h at sub-level l' (group g') uses the full-size zeta index 2^(l'+1) + h*2^l' + g'.
+//   uni[UNI_FWD][32h + k]   k in [1,32): forward zetas of the rows pass of half h;   [0] = zeta[1] (split level)
+//   uni[UNI_INV_*][32h + k] k in [1,32): inverse zetas of the rows pass of half h;   [0] = K, [32] = K * zeta[1]^-1
+//   block[kind] = [per-lane forward table of half 0][of half 1]; the inverse cols pass of half h reads
+//   the table of half 1-h mirrored (zeta[k]^-1 = -zeta[mirror(k)], and the mirror lives in the other half).
+inline void build_tables_split(HostTables* T) {
+    const RtParams p = make_rt<SET_P_III_H>();
+    const RtParams f = make_rt<SET_P_III>();
+    T->p = p;
+    const uint32_t q = f.q, nf = f.n;
+    std::vector<uint32_t> psi_pow(2 * nf);
+    psi_pow[0] = 1;
+    for (uint32_t e = 1; e < 2 * nf; e++) psi_pow[e] = c_mulmod(psi_pow[e - 1], f.psi, q);
+    auto zf = [&](uint32_t k) { return psi_pow[c_bitrev(k, f.logn)]; };
+    auto zi = [&](uint32_t k) { return psi_pow[(2 * nf - c_bitrev(k, f.logn)) % (2 * nf)]; };
+    auto full_index = [&](uint32_t h, uint32_t ksub) {  // ksub = 2^l' + g'
+        const uint32_t lp = c_log2(ksub + 1) - 1;     // floor(log2 ksub)
+        return (2u << lp) + h * (1u << lp) + (ksub - (1u << lp));
+    };
+    for (int kind = 0; kind < UNI_KINDS; kind++)
+        for (int k = 0; k < UNI_MAX; k++) T->uni[kind][k] = TwPair{0, 0};
+    const uint32_t K_plain = f.n_inv, K_fused = c_mulmod(f.n_inv, f.r_modq, q);
+    for (uint32_t h = 0; h < 2; h++)
+        for (uint32_t k = 1; k < 32; k++) {
+            T->uni[UNI_FWD][32 * h + k] = tw_unsigned(zf(full_index(h, k)), q);
+            T->uni[UNI_INV_PLAIN][32 * h + k] = T->uni[UNI_INV_FUSED][32 * h + k] = tw_unsigned(zi(full_index(h, k)), q);
+        }
+    T->uni[UNI_FWD][0] = tw_unsigned(zf(1), q);
+    T->uni[UNI_INV_PLAIN][0] = tw_unsigned(K_plain, q);
+    T->uni[UNI_INV_FUSED][0] = tw_unsigned(K_fused, q);
+    T->uni[UNI_INV_PLAIN][32] = tw_unsigned(c_mulmod(zi(1), K_plain, q), q);
+    T->uni[UNI_INV_FUSED][32] = tw_unsigned(c_mulmod(zi(1), K_fused, q), q);
+    const uint32_t blocks = p.n / p.E;
+    T->fwd_quads = 2 * p.slot_pairs * blocks;
+    T->inv_quads = T->scale_quads = 0;
+    for (int kind = 0; kind < 2; kind++) {
+        std::vector<TwQuad>& B = T->block[kind];
+        B.assign(T->fwd_quads, TwQuad{0, 0, 0, 0});
+        for (uint32_t h = 0; h < 2; h++)
+            for (uint32_t jb = 0; jb < blocks; jb++) {
+                uint32_t slot = 0;
+                for (uint32_t l = p.lb1; l < p.logn; l++) {
+                    const uint32_t G = p.E >> (p.logn - l);
+                    for (uint32_t g = 0; g < G; g++, slot++)
+                        put_slot(B, (size_t)h * p.slot_pairs * blocks, slot, blocks, jb,
+                                 tw_unsigned(zf(full_index(h, (1u << l) + jb * G + g)), q));
+                }
+            }
+    }
+}
+
 }  // namespace qt

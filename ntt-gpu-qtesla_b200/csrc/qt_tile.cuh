@@ -45,10 +45,10 @@ namespace qt {
 #if defined(__CUDACC__)
 // Uniform twiddles of the rows pass.  Indexed only with compile-time constants after unrolling,
 // so they are consumed as constant-bank operands of IMAD (no load instruction).
-__constant__ TwPair c_uni[NUM_SETS][UNI_KINDS][UNI_MAX];
+__constant__ TwPair c_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
 #endif
 #if !defined(__CUDA_ARCH__)
-extern TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX];  // host mirror (table upload / emulation)
+extern TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];  // host mirror (table upload / emulation)
 #endif
 
 template <int SET, int KIND> QT_HD TwPair uni_tw(int k) {
@@ -92,7 +92,7 @@ template <int SET> struct Tile {
     static constexpr uint32_t INV_SLOTS = E - 1;                      // rows levels of the DIT inverse: 1+2+..+E/2
     static constexpr uint32_t INV_QUADS = LAZY ? ((INV_SLOTS + 1) / 2) * LPP : 0;
     static constexpr uint32_t SCALE_QUADS = LAZY ? (E / 2) * LPP : 0;
-    static constexpr uint32_t TABLE_QUADS = TW_QUADS + INV_QUADS + SCALE_QUADS;
+    static constexpr uint32_t TABLE_QUADS = C::HALVES * TW_QUADS + INV_QUADS + SCALE_QUADS;
     struct LanePtrs { const TwQuad *fwd, *inv, *scale; };
     static QT_HD LanePtrs lane_ptrs(const TwQuad* tab, uint32_t lane) {
         if (LAZY) return LanePtrs{tab + lane % BLOCKS, tab + TW_QUADS + lane % LPP, tab + TW_QUADS + INV_QUADS + lane % LPP};
@@ -159,14 +159,16 @@ template <int SET> struct Tile {
 
     // ---- transforms on one lane's registers ---------------------------------------------------
     // rows layout, forward levels 0..LB1-1 (register distance E/2 .. 1)
-    static QT_HD void fwd_rows(uint32_t (&v)[E]) {
+    // ub: offset into the uniform tables (split tiles: 32 * half, a run-time value; otherwise 0 and
+    // every index is a compile-time constant)
+    static QT_HD void fwd_rows(uint32_t (&v)[E], uint32_t ub = 0) {
 #pragma unroll
         for (uint32_t l = 0; l < LB1; l++) {
             const uint32_t half = E >> (l + 1);
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {  // flat butterfly index: constant trip count
                 const uint32_t g = i / half, j = i % half;
-                ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>((1u << l) + g));
+                ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>(ub + (1u << l) + g));
             }
         }
     }
@@ -235,7 +237,7 @@ template <int SET> struct Tile {
     //          n^-1 psi^-i — the reference's invPhi table (NTT.cu:1846-1849) — from p.scale; the FUSED
     //          scale table also carries the 2^32 of the pointwise Montgomery product.
     //  Harvey: merged Gentleman-Sande with uniform twiddles, scale folded into the last level.
-    template <int KIND> static QT_HD void inv_rows(uint32_t (&v)[E], const LanePtrs& p) {
+    template <int KIND> static QT_HD void inv_rows(uint32_t (&v)[E], const LanePtrs& p, uint32_t ub = 0) {
         if (LAZY) {
 #pragma unroll
             for (uint32_t k = 0; k < LB1; k++) {
@@ -258,8 +260,8 @@ template <int SET> struct Tile {
                     const uint32_t g = i / half, j = i % half;
                     uint32_t& a = v[2 * g * half + j];
                     uint32_t& b = v[2 * g * half + j + half];
-                    const TwPair t = uni_tw<SET, KIND>((1u << l) + g);
-                    if (l != 0) {
+                    const TwPair t = uni_tw<SET, KIND>(ub + (1u << l) + g);
+                    if (l != 0 || C::SPLIT) {  // (split tiles: the last level is split_inv's)
                         const uint32_t s_ = a + b, d = a - b + TWO_Q;
                         a = csub(s_, TWO_Q);
                         b = mul_shoup(d, t);
@@ -271,6 +273,20 @@ template <int SET> struct Tile {
                 }
             }
         }
+    }
+
+    // ---- split tiles (C::SPLIT): the level that joins the two halves --------------------------------
+    // forward: (lo[i], hi[i]) -> (lo + zeta1 hi, lo - zeta1 hi), the first Cooley-Tukey level of the
+    // full-size transform; afterwards lo / hi are the inputs of the two independent half transforms
+    static QT_HD void split_fwd(uint32_t (&lo)[E], uint32_t (&hi)[E]) {
+#pragma unroll
+        for (uint32_t r = 0; r < E; r++) ct(lo[r], hi[r], uni_tw<SET, UNI_FWD>(0));
+    }
+    // inverse: the last Gentleman-Sande level with the output scale K folded in; inputs < 2q, outputs canonical
+    template <int KIND> static QT_HD void split_inv(uint32_t& a, uint32_t& b) {
+        const uint32_t s_ = a + b, d = a - b + TWO_Q;
+        a = csub(mul_shoup(s_, uni_tw<SET, KIND>(0)), Q);
+        b = csub(mul_shoup(d, uni_tw<SET, KIND>(32)), Q);
     }
 
     // NTT-domain product of two forward outputs: a*b*2^-32 mod q (LAZY: signed, |.| < q; Harvey: [0,2q))

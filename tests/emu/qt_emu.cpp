@@ -12,7 +12,7 @@
 #include "../../ntt-gpu-qtesla_b200/csrc/qt_nussbaumer.cuh"
 
 namespace qt {
-TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX];
+TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
 }
 using namespace qt;
 
@@ -186,6 +186,70 @@ template <int SET> struct Emu {
     }
 };
 
+// k_polymul_split lane by lane: n=2048 as two 1024-point halves on the SET_P_III_H tile
+struct EmuSplit {
+    using T = Tile<SET_P_III_H>;
+    static constexpr uint32_t E = T::E, HALF = T::N;
+    HostTables tab;
+    EmuSplit() {
+        build_tables_split(&tab);
+        memcpy(h_uni[SET_P_III_H], tab.uni, sizeof(tab.uni));
+    }
+    void polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+        alignas(16) static uint32_t A[2 * 1024], B[2 * 1024];
+        const TwQuad* s_tw = tab.block[1].data();
+        std::vector<uint32_t> V(32 * E), H(32 * E);
+        auto v = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&V[lane * E]); };
+        auto hi = [&](uint32_t lane) -> uint32_t(&)[E] { return *reinterpret_cast<uint32_t(*)[E]>(&H[lane * E]); };
+        for (size_t tile = 0; tile < batch; tile++) {
+            for (int op = 0; op < 2; op++) {
+                uint32_t* st = op ? B : A;
+                memcpy(st, (op ? y : x) + tile * 2 * HALF, 2 * HALF * sizeof(uint32_t));  // the bulk copy
+                for (uint32_t l = 0; l < 32; l++)
+                    for (uint32_t r = 0; r < E; r++) { v(l)[r] = st[l + 32 * r]; hi(l)[r] = st[HALF + l + 32 * r]; }
+                for (uint32_t l = 0; l < 32; l++) {
+                    T::split_fwd(v(l), hi(l));
+                    T::sts_rows(hi(l), st + HALF, l);
+                }
+                for (uint32_t h = 0; h < 2; h++) {
+                    uint32_t* sh = st + h * HALF;
+                    for (uint32_t l = 0; l < 32; l++) {
+                        if (h) T::lds_rows(v(l), sh, l);
+                        T::fwd_rows(v(l), 32 * h);
+                        T::sts_rows(v(l), sh, l);
+                    }
+                    for (uint32_t l = 0; l < 32; l++) {
+                        T::lds_cols(v(l), sh, l);
+                        T::fwd_cols(v(l), s_tw + h * T::TW_QUADS + l);
+                    }
+                    if (op == 0) {
+                        for (uint32_t l = 0; l < 32; l++) T::sts_cols(v(l), sh, l);
+                        continue;
+                    }
+                    for (uint32_t l = 0; l < 32; l++) {
+                        T::pointwise_mont_stash(v(l), A + h * HALF, l);
+                        T::inv_cols(v(l), s_tw + (1 - h) * T::TW_QUADS + (T::BLOCKS - 1 - l));
+                    }
+                    for (uint32_t l = 0; l < 32; l++) T::sts_cols(v(l), sh, l);
+                    for (uint32_t l = 0; l < 32; l++) {
+                        T::lds_rows(v(l), sh, l);
+                        T::template inv_rows<UNI_INV_FUSED>(v(l), typename T::LanePtrs{nullptr, nullptr, nullptr}, 32 * h);
+                        if (h == 0) T::sts_rows(v(l), sh, l);
+                    }
+                }
+            }
+            uint32_t* zt = z + tile * 2 * HALF;
+            for (uint32_t l = 0; l < 32; l++)
+                for (uint32_t r = 0; r < E; r++) {
+                    uint32_t a = B[T::swz(T::row_off(l, r))];
+                    T::template split_inv<UNI_INV_FUSED>(a, v(l)[r]);
+                    zt[l + 32 * r] = a;
+                    zt[HALF + l + 32 * r] = v(l)[r];
+                }
+        }
+    }
+};
+
 template <int SET> Emu<SET>& emu() {
     static Emu<SET> e;
     return e;
@@ -259,6 +323,11 @@ template <int SET, int RING> int emu_nussbaumer(const uint32_t* x, const uint32_
 extern "C" {
 int qtemu_polymul(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
     EMU_DISPATCH(set, polymul(x, y, z, batch));
+    return 0;
+}
+int qtemu_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    static EmuSplit e;
+    e.polymul(x, y, z, batch);
     return 0;
 }
 int qtemu_forward(int set, uint32_t* a, size_t batch) {

@@ -24,6 +24,7 @@ def emu():
     L.qtemu_forward.argtypes = [C.c_int, u, C.c_size_t]
     L.qtemu_inverse.argtypes = [C.c_int, u, C.c_size_t]
     L.qtemu_forward_natural.argtypes = [C.c_int, u, C.c_size_t]
+    L.qtemu_polymul_split.argtypes = [u, u, u, C.c_size_t]
     L.qtemu_inverse_natural.argtypes = [C.c_int, u, C.c_size_t]
     L.qtemu_nussbaumer.argtypes = [C.c_int, u, u, u, C.c_size_t, C.c_int]
     return L
@@ -48,6 +49,21 @@ def test_emulated_kernel_equals_oracle(emu, oracle, s):
     g = f.copy()
     emu.qtemu_inverse(s, _p(g), B)
     assert np.array_equal(g, x)
+
+
+def test_emulated_split_kernel_equals_oracle(emu, oracle):
+    """k_polymul_split: n=2048 as two 1024-point halves joined by one level (SET_P_III_H tile)."""
+    p = oracle.params(SET_P_III)
+    B = 4
+    rng = np.random.default_rng(77)
+    x = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    y = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    x[: p.n] = p.q - 1
+    y[: p.n] = p.q - 1
+    x[p.n: 2 * p.n] = 0
+    z = np.zeros_like(x)
+    assert emu.qtemu_polymul_split(_p(x), _p(y), _p(z), B) == 0
+    assert np.array_equal(z, oracle.polymul(SET_P_III, x, y))
 
 
 @pytest.mark.parametrize("s", ALL_SETS)

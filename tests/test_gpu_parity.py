@@ -33,11 +33,16 @@ def rand_pair(q, words, seed):
     return rng.integers(0, q, words, dtype=np.uint32), rng.integers(0, q, words, dtype=np.uint32)
 
 
-@pytest.mark.parametrize("variant", [1, 2])   # 1 = direct coalesced loads, 2 = TMA bulk copies + mbarrier
+# 0 = automatic, 1 = direct coalesced loads, 2 = TMA bulk copies + mbarrier, 3 = n=2048 as two halves
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("s", ALL_SETS)
 @pytest.mark.parametrize("B", [1, 2, 3, 67, 1000, 5001])
 def test_fused_polymul_equals_oracle(engines, oracle, s, B, variant):
     eng = engines[s]
+    if variant == 3 and s != 3:
+        with pytest.raises(Exception):
+            eng.set_fused_variant(3)   # the split tile exists for n=2048 only
+        return
     eng.set_fused_variant(variant)
     try:
         x, y = rand_pair(eng.q, B * eng.n, 100 * s + B)
@@ -57,6 +62,8 @@ def test_fused_variants_agree_at_full_size(engines, s):
     eng.set_fused_variant(1); eng.polymul(x, y, z1)
     eng.set_fused_variant(2); eng.polymul(x, y, z2)
     eng.set_fused_variant(0); eng.synchronize()
+    assert torch.equal(z1, z2)
+    eng.polymul(x, y, z2); eng.synchronize()      # automatic choice (n=2048: the split-tile kernel)
     assert torch.equal(z1, z2)
 
 
@@ -295,13 +302,14 @@ def test_cxx_harness_reference_command_line():
     assert out.returncode == 0 and str((2 - 2048) % 856145921) in out.stdout
 
 
-@pytest.mark.parametrize("s", ALL_SETS)
-def test_cached_transform_product(engines, oracle, s):
+@pytest.mark.parametrize("B", [41, 2000])
+@pytest.mark.parametrize("s,variant", [(0, 0), (1, 0), (2, 0), (3, 0), (3, 2)])  # n=2048: split tile (auto) and 64-wide tile
+def test_cached_transform_product(engines, oracle, s, variant, B):
     """qTESLA-shaped caller: one public polynomial a (transformed once) times many y, incl. sparse ternary y."""
     import torch
     eng = engines[s]
+    eng.set_fused_variant(variant)
     n, q = eng.n, eng.q
-    B = 41
     rng = np.random.default_rng(70 + s)
     a = rng.integers(0, q, n, dtype=np.uint32)
     y = rng.integers(0, q, B * n, dtype=np.uint32)
@@ -323,6 +331,7 @@ def test_cached_transform_product(engines, oracle, s):
     eng.ntt_forward(taa)
     eng.polymul_ntt(taa, ty, tz, broadcast=False)
     eng.synchronize()
+    eng.set_fused_variant(0)
     assert np.array_equal(tz.cpu().numpy().view(np.uint32), oracle.polymul(s, aa, y))
 
 

@@ -47,6 +47,12 @@ for name in args.sets.split(","):
             eng.fill_uniform(ah, 3, 0); eng.ntt_forward(ah)
         r = timeit(lambda: eng.polymul_ntt(ah, y, z, True, B), args.steps)
         print(f"{name:6s} cached a_hat (broadcast): {r/1e6:8.2f} M polymul/s", flush=True)
+        xh = x.clone()
+        with torch.cuda.stream(stream):
+            eng.ntt_forward(xh, B)
+        r = timeit(lambda: eng.polymul_ntt(xh, y, z, False, B), args.steps)
+        print(f"{name:6s} cached a_hat (per product): {r/1e6:8.2f} M polymul/s", flush=True)
+        del xh
     except Exception as ex:
         print(f"{name:6s} cached: {ex}")
     w = x.clone()
