@@ -6,7 +6,7 @@
 #include <cstdio>
 #include <vector>
 #include "../ntt-gpu-qtesla_b200/csrc/qt_tile.cuh"
-namespace qt { TwPair h_uni[NUM_SETS][UNI_KINDS][UNI_MAX]; }
+namespace qt { TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX]; }
 using namespace qt;
 using T = Tile<SET_III>;
 
