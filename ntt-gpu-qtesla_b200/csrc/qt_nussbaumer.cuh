@@ -48,13 +48,47 @@ template <int SET> struct NussCfg {
 template <int SET, int RING> struct NussOps;
 
 template <int SET> struct NussOps<SET, 0> {  // Z/(2^32-1), NTT.cu:102-134
-    static QT_HD uint32_t add(uint32_t a, uint32_t b) { uint32_t t = a + b; return t + (uint32_t)(t < a); }
-    static QT_HD uint32_t sub(uint32_t a, uint32_t b) { return (a - b) - (uint32_t)(b > a); }
-    static QT_HD uint32_t norm(uint32_t a) { return a + (uint32_t)(a == 0xFFFFFFFFu); }
+    // End-around-carry arithmetic.  On the device each operation is the two-instruction carry chain it
+    // is (IADD3 with carry-out + IADD3.X); the C++ forms below are what the host emulator executes and
+    // what the compiler otherwise turns into compare/select sequences twice as long.
+    static QT_HD uint32_t add(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        uint32_t r;
+        asm("add.cc.u32 %0, %1, %2;\n\taddc.u32 %0, %0, 0;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
+#else
+        uint32_t t = a + b;
+        return t + (uint32_t)(t < a);
+#endif
+    }
+    static QT_HD uint32_t sub(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        uint32_t r;
+        asm("sub.cc.u32 %0, %1, %2;\n\tsubc.u32 %0, %0, 0;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
+#else
+        return (a - b) - (uint32_t)(b > a);
+#endif
+    }
+    static QT_HD uint32_t norm(uint32_t a) {  // 0xFFFFFFFF -> 0 (the carry of a + 1)
+#if defined(__CUDA_ARCH__)
+        uint32_t r;
+        asm("add.cc.u32 %0, %1, 1;\n\taddc.u32 %0, %1, 0;" : "=&r"(r) : "r"(a));
+        return r;
+#else
+        return a + (uint32_t)(a == 0xFFFFFFFFu);
+#endif
+    }
     static QT_HD uint32_t neg(uint32_t a) { return norm(0xFFFFFFFFu - a); }
+    // halving adds the (odd) modulus to an odd value first: (a + 2^32 - 1) / 2 = (a >> 1) + 2^31, i.e. a
+    // rotation to the right by one bit (2^32 = 1 in this ring)
     static QT_HD uint32_t half(uint32_t a) {
         a = norm(a);
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_r(a, a, 1);
+#else
         return (uint32_t)(((uint64_t)a + (uint64_t)(uint32_t)(0u - (a & 1u))) >> 1);
+#endif
     }
     static QT_HD uint32_t fold(uint64_t t) { return add((uint32_t)t, (uint32_t)(t >> 32)); }
 };
@@ -176,7 +210,22 @@ template <int SET, int RING> struct Nuss {
                     xr[k] = (uint32_t)((acc0 % Q + acc1 % Q) % Q);
                 }
             }
-        } else {  // R == 64, Z_q only: y row doubled in place [q - y | y], x in registers
+        } else if (RING == 0) {  // R == 64, ring 2^32-1: x in registers, y indexed in shared memory
+            uint32_t x[64];
+#pragma unroll
+            for (uint32_t j = 0; j < 64; j++) x[j] = xr[j];
+            for (uint32_t k = 0; k < 64; k++) {  // naive (NTT.cu:147-165) with n = 64: chains A (j<=k), B (j>k) in j order
+                uint32_t A = NussOps<SET, 0>::fold((uint64_t)x[0] * yr[k]), B = 0;
+#pragma unroll
+                for (uint32_t j = 1; j < 64; j++) {
+                    const bool in_a = j <= k;
+                    const uint32_t t = NussOps<SET, 0>::fold((uint64_t)x[j] * yr[(k - j) & 63u] + (in_a ? A : B));
+                    A = in_a ? t : A;
+                    B = in_a ? B : t;
+                }
+                xr[k] = NussOps<SET, 0>::sub(A, B);
+            }
+        } else {  // R == 64, Z_q: y row doubled in place [q - y | y], x in registers
             uint32_t x[64];
 #pragma unroll
             for (uint32_t j = 0; j < 64; j++) x[j] = xr[j];
@@ -465,7 +514,7 @@ template <int SET> int nuss_setup(int num_sms, int* grid) {
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nussbaumer<SET, 1>, K::THREADS, K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    if (K::R == 32) {
+    {
         int occ0 = 0;
         e = cudaFuncSetAttribute(k_nussbaumer<SET, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
@@ -492,9 +541,7 @@ int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z,
     const size_t groups = (batch + K::P - 1) / K::P;
     const int grid = (int)(groups < (size_t)max_grid ? groups : (size_t)max_grid);
     if (ring == 0) {
-        if (K::R != 32) return -4;  // ring 2^32-1 is provided for the 32-column splits (n=512, 1024) only
-        if constexpr (K::R == 32)
-            k_nussbaumer<SET, 0><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+        k_nussbaumer<SET, 0><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
     } else {
         k_nussbaumer<SET, 1><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
     }

@@ -262,7 +262,6 @@ template <int SET> Emu<SET>& emu() {
 template <int SET, int RING> int emu_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
     using K = NussCfg<SET>;
     using NU = Nuss<SET, RING>;
-    if (RING == 0 && K::R != 32) return -4;
     std::vector<uint32_t> smem(K::P * K::POLY_WORDS);
     constexpr uint32_t WARPS = K::THREADS / 32;
     const size_t ngroups = (batch + K::P - 1) / K::P;

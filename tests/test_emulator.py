@@ -107,7 +107,4 @@ def test_emulated_nussbaumer_equals_oracle(emu, oracle, s):
     yr[2 * p.n: 3 * p.n] = 0
     yr[2 * p.n + rng.choice(p.n, 40, replace=False)] = 0xFFFFFFFE
     rc = emu.qtemu_nussbaumer(s, _p(xr), _p(yr), _p(z), B, 0)               # ring 2^32-1, bit-exact incl. zeros
-    if p.n == 2048:
-        assert rc == -4   # the 64-column split is provided over Z_q only
-    else:
-        assert rc == 0 and np.array_equal(z, oracle.nussbaumer(p.n, xr, yr))
+    assert rc == 0 and np.array_equal(z, oracle.nussbaumer(p.n, xr, yr))

@@ -266,6 +266,30 @@ def test_nussbaumer_ring_equals_oracle(engines, oracle, qt):
     assert list(z[:3]) == [4294966273, 4294966275, 4294966277]
 
 
+@pytest.mark.parametrize("s", [0, 2, 3])
+def test_nussbaumer_ring_other_sizes(engines, oracle, golden, qt, s):
+    """n-generic Nussbaumer over Z/(2^32-1) (n = 512: 16x32 split, n = 2048: 32x64 split), SURVEY.md 8a/8c."""
+    import torch
+    eng = engines[s]
+    n = eng.n
+    rng = np.random.default_rng(90 + s)
+    B = 7
+    x = rng.integers(0, 2 ** 32, B * n, dtype=np.uint32)
+    y = rng.integers(0, 2 ** 32, B * n, dtype=np.uint32)
+    xx, yy, _ = oracle.xorshift_pair(eng.q, n)                       # the golden stream of SURVEY.md 8c
+    x[:n] = xx; y[:n] = yy
+    x[n:2 * n] = 0xFFFFFFFF                                          # non-normalised zeros
+    y[2 * n:3 * n] = 0; y[2 * n + rng.choice(n, 40, replace=False)] = 0xFFFFFFFE   # sparse ternary (-1)
+    tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda(); tz = torch.empty_like(tx)
+    eng.nussbaumer(tx, ty, tz, qt.RING_2P32M1)
+    eng.synchronize()
+    z = tz.cpu().numpy().view(np.uint32)
+    assert np.array_equal(z, oracle.nussbaumer(n, x, y))
+    z0 = z[:n].copy(); z0[z0 == 0xFFFFFFFF] = 0
+    name = {0: "qTESLA-I", 2: "qTESLA-p-I", 3: "qTESLA-p-III"}[s]
+    assert sha(z0) == golden[name + "_ring_schoolbook_b1_sha256"]
+
+
 @pytest.mark.parametrize("s", ALL_SETS)
 def test_nussbaumer_modq_equals_ntt(engines, oracle, qt, s):
     import torch
