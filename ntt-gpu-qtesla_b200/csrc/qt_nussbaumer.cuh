@@ -22,6 +22,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <type_traits>
 
 #include "qt_tile.cuh"
 
@@ -100,6 +101,19 @@ template <int SET> struct NussOps<SET, 1> {  // Z_q, operands canonical
     static QT_HD uint32_t sub(uint32_t a, uint32_t b) { return csub(a - b + Q); }
     static QT_HD uint32_t neg(uint32_t a) { return csub(Q - a); }
     static QT_HD uint32_t half(uint32_t a) { return (a + (Q & (0u - (a & 1u)))) >> 1; }
+};
+
+// Z_q for q < 2^25 inside the warp-resident kernel: two's-complement residues and NO reduction in the
+// stage phases.  Forward: |v| <= 2^LOGM q.  Products accumulate in a signed 64-bit register
+// (32 terms of < (2^LOGM q)^2 each); one signed Montgomery reduction and one signed Shoup multiplication by
+// 2^32 * 2^-(LOGM+1) bring every Z row back to [-q/2, 3q/2) and pay for the halvings of ALL inverse stages
+// in advance, so the inverse is additions only: |v| < 1.5 * 2^(LOGM+1) q, recombination doubles once more.
+template <int SET> struct NussOpsLazy {
+    static constexpr uint32_t Q = Cfg<SET>::Q;
+    static QT_HD uint32_t add(uint32_t a, uint32_t b) { return a + b; }
+    static QT_HD uint32_t sub(uint32_t a, uint32_t b) { return a - b; }
+    static QT_HD uint32_t neg(uint32_t a) { return 0u - a; }
+    static QT_HD uint32_t half(uint32_t a) { return a; }  // deferred: folded into the post-product constant
 };
 
 template <int SET, int RING> struct Nuss {
@@ -326,9 +340,13 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
 // factor 2^-32 is removed by one Shoup multiplication per output coefficient at the very end.
 template <int SET, int RING> struct NussWarp {
     using K = NussCfg<SET>;
-    using O = NussOps<SET, RING>;
     using T = Tile<SET>;
+    static constexpr bool LAZYQ = (RING == 1) && T::LAZY;  // signed-lazy Z_q (see NussOpsLazy)
+    using O = typename std::conditional<LAZYQ, NussOpsLazy<SET>, NussOps<SET, RING>>::type;
     static constexpr uint32_t M = K::M, LOGM = K::LOGM, ROWS = K::ROWS, Q = K::Q;
+    // ranges of the lazy variant: 32 products of two forward outputs in an int64; 3 * 2^(LOGM+1) q in an int32
+    static_assert(!LAZYQ || (uint64_t)Q * Q < (1ull << (63 - 5 - 2 * LOGM)), "lazy product accumulator");
+    static_assert(!LAZYQ || ((uint64_t)(3u << (LOGM + 1)) * Q < (1ull << 31)), "lazy inverse range");
     static constexpr uint32_t RS = 33;                                   // row stride in shared memory
     static constexpr uint32_t WARP_WORDS = 2 * ROWS * RS;                // X rows then Y rows
     static constexpr uint32_t WARPS = 12;  // 12 x 16.9 KiB of rows, <= 170 registers: one CTA per SM
@@ -396,6 +414,22 @@ template <int SET, int RING> struct NussWarp {
                 }
                 xr[k] = NussOps<SET, 0>::sub(A, B);
             }
+        } else if (LAZYQ) {
+            // 2^32 (the Montgomery factor) times 2^-(LOGM+1) (every halving of the inverse stages), signed Shoup form
+            constexpr uint32_t FIX = c_mulmod(T::C::R_MODQ, c_powmod((Q + 1) / 2, LOGM + 1, Q), Q);
+            const TwPair fix = tw_signed_c(FIX, Q);
+#pragma unroll
+            for (uint32_t k = 0; k < 32; k++) {
+                int64_t acc = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) {
+                    const int64_t pr = (int64_t)(int32_t)x[j] * (int64_t)(int32_t)((j <= k) ? y[(k - j) & 31] : y[(32 + k - j) & 31]);
+                    acc = (j <= k) ? acc + pr : acc - pr;  // wrapped terms enter negated
+                }
+                const uint32_t m = (uint32_t)acc * (0u - T::C::QINV_NEG);                 // lo(acc) * q^-1
+                const uint32_t red = (uint32_t)(acc >> 32) - (uint32_t)mulhi32s(m, Q);   // acc * 2^-32, |red| < 2^30
+                xr[k] = T::smul_shoup(red, fix);                                          // [-q/2, 3q/2)
+            }
         } else {
             uint32_t ny[32];
 #pragma unroll
@@ -429,7 +463,7 @@ __global__ void __launch_bounds__(NussWarp<SET, RING>::WARPS * 32)
 k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
     using W = NussWarp<SET, RING>;
     using K = NussCfg<SET>;
-    using O = NussOps<SET, RING>;
+    using O = typename W::O;
     using T = Tile<SET>;
     static_assert(K::R == 32, "warp-resident Nussbaumer needs 32 columns");
     extern __shared__ uint4 nuss_smem_raw[];
@@ -475,7 +509,8 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
                 const uint32_t i = 4 * c + k;
                 const uint32_t up = __shfl_sync(0xffffffffu, v[K::M + i], (lane - 1) & 31u);
                 uint32_t r = (lane == 0) ? O::sub(v[i], up) : O::add(v[i], up);
-                if (RING == 1) r = T::csub(T::mul_shoup(r, rfix), T::Q);
+                if (W::LAZYQ) r = T::scanon(T::smul_shoup(r, TwPair{1u, T::C::MU32}));  // any |r| < 2^31 -> [0, q)
+                else if (RING == 1) r = T::csub(T::mul_shoup(r, rfix), T::Q);
                 o[k] = r;
             }
             gz[c] = make_uint4(o[0], o[1], o[2], o[3]);

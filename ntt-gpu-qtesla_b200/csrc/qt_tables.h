@@ -45,6 +45,15 @@ inline TwPair tw_signed(uint32_t w, uint32_t q) {
     return TwPair{(uint32_t)(int32_t)wc, (uint32_t)(int32_t)fl};
 }
 
+// the same as a compile-time constant usable in device code
+QT_CHD TwPair tw_signed_c(uint32_t w, uint32_t q) {
+    const int64_t wc = (w > q / 2) ? (int64_t)w - (int64_t)q : (int64_t)w;
+    const int64_t num = wc * (int64_t)(1ll << 32);
+    int64_t fl = num / (int64_t)q;
+    if (num % (int64_t)q != 0 && num < 0) fl -= 1;
+    return TwPair{(uint32_t)(int32_t)wc, (uint32_t)(int32_t)fl};
+}
+
 inline void put_slot(std::vector<TwQuad>& v, size_t base, uint32_t slot, uint32_t stride, uint32_t lane, TwPair t) {
     TwQuad& qd = v[base + (size_t)(slot / 2) * stride + lane];
     if (slot & 1) { qd.w1 = t.w; qd.ws1 = t.ws; }

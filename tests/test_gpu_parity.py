@@ -295,7 +295,13 @@ def test_nussbaumer_modq_equals_ntt(engines, oracle, qt, s):
     import torch
     eng = engines[s]
     B = 9
-    x, y = rand_pair(eng.q, B * eng.n, 555 + s)
+    n, q = eng.n, eng.q
+    x, y = rand_pair(q, B * n, 555 + s)
+    # worst cases for the unreduced (lazy) stage arithmetic: everything q-1; q-1 against alternating 0 / q-1
+    x[:n] = q - 1; y[:n] = q - 1
+    x[n:2 * n] = q - 1; y[n:2 * n] = np.where(np.arange(n) % 2 == 0, q - 1, 0)
+    x[2 * n:3 * n] = np.where(np.arange(n) % 64 < 32, q - 1, 0); y[2 * n:3 * n] = q - 1
+    x[3 * n:4 * n] = 0
     tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda(); tz = torch.empty_like(tx)
     try:
         eng.nussbaumer(tx, ty, tz, qt.RING_MODQ)
