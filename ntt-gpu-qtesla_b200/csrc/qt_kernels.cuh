@@ -160,7 +160,7 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
     uint64_t* bar_b = bar_a + 1;
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     const size_t stride = (size_t)gridDim.x * NW;
-    size_t tile = (size_t)blockIdx.x * NW + warp;
+    size_t tile = (size_t)warp * gridDim.x + blockIdx.x;  // SM-interleaved: a partial last round spreads over all SMs
 
     auto issue = [&](const uint32_t* g, uint32_t* st, uint64_t* bar, size_t t) {  // one lane
         const size_t p0 = t * T::PPW;
@@ -267,7 +267,7 @@ k_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
     uint64_t* bar_a = s_bar + 2 * warp;
     uint64_t* bar_b = bar_a + 1;
     const size_t stride = (size_t)gridDim.x * NW;
-    size_t tile = (size_t)blockIdx.x * NW + warp;  // one polynomial per tile
+    size_t tile = (size_t)warp * gridDim.x + blockIdx.x;  // SM-interleaved: a partial last round spreads over all SMs  // one polynomial per tile
     auto issue = [&](const uint32_t* g, uint32_t* st, uint64_t* bar, size_t t) {  // one lane
         mbar_expect_tx(bar, G::WORDS * (uint32_t)sizeof(uint32_t));
         bulk_g2s(st, g + t * G::WORDS, G::WORDS * (uint32_t)sizeof(uint32_t), bar);
@@ -404,7 +404,7 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
     uint64_t* bar0 = s_bar + 2 * warp;
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     const size_t stride = (size_t)gridDim.x * NW;
-    size_t tile = (size_t)blockIdx.x * NW + warp;
+    size_t tile = (size_t)warp * gridDim.x + blockIdx.x;  // SM-interleaved: a partial last round spreads over all SMs
     auto issue = [&](uint32_t* st, uint64_t* bar, size_t t) {
         const size_t p0 = t * T::PPW;
         const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);
@@ -606,7 +606,7 @@ k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     uint64_t* bar0 = s_bar + 2 * warp;
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
     const size_t stride = (size_t)gridDim.x * NW;
-    size_t tile = (size_t)blockIdx.x * NW + warp;
+    size_t tile = (size_t)warp * gridDim.x + blockIdx.x;  // SM-interleaved: a partial last round spreads over all SMs
     auto issue = [&](uint32_t* st, uint64_t* bar, size_t t) {
         const size_t p0 = t * T::PPW;
         const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);

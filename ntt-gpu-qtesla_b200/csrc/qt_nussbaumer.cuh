@@ -472,7 +472,7 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
     uint32_t* sy = sx + W::ROWS * W::RS;
     // 2^32 mod q with its Shoup companion: removes the Montgomery factor of the products
     const TwPair rfix{T::C::R_MODQ, (uint32_t)(((uint64_t)T::C::R_MODQ << 32) / T::Q)};
-    for (size_t p = (size_t)blockIdx.x * W::WARPS + warp; p < batch; p += (size_t)gridDim.x * W::WARPS) {
+    for (size_t p = (size_t)warp * gridDim.x + blockIdx.x; p < batch; p += (size_t)gridDim.x * W::WARPS) {  // SM-interleaved
         const uint32_t* gx = x + p * K::N;
         const uint32_t* gy = y + p * K::N;
         uint32_t v[W::ROWS];
