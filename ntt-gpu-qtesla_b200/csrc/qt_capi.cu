@@ -49,7 +49,7 @@ struct qt_ctx {
     bool split_ok = false;
     int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged, 3 split tile (n=2048)
     size_t smem_fused = 0, smem_one = 0, smem_tma = 0;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     // host pipeline (qt_polymul_host): lazily created
     static constexpr int PIPE = 8;  // maximum number of pipeline slots
     int pipe_slots = 3;             // slots in use
@@ -57,6 +57,16 @@ struct qt_ctx {
     uint32_t* pipe_buf[PIPE] = {};  // x | y per slot, z overwrites x
     size_t pipe_polys = 0;
     bool pipe_ready = false;
+    // staged pipeline for PAGEABLE host buffers (what a malloc-ing caller such as the reference's main.cu
+    // passes): worker threads copy chunks through pinned staging buffers, lazily created
+    static constexpr int STAGE = 16;  // maximum number of workers
+    int stage_workers = 0;           // 0 = not decided yet
+    int stage_share = 1;             // contexts sharing the host cores (qt_polymul_host_multi)
+    cudaStream_t stage_stream[STAGE] = {};
+    uint32_t* stage_dev[STAGE] = {};   // x | y per worker (z overwrites x)
+    uint32_t* stage_host[STAGE] = {};  // pinned mirror of the same
+    size_t stage_polys = 0;
+    bool stage_ready = false;
 };
 
 namespace {
@@ -266,6 +276,51 @@ void release_pipe(qt_ctx* c) {
     c->pipe_ready = false;
 }
 
+void release_stage(qt_ctx* c) {
+    for (int i = 0; i < qt_ctx::STAGE; i++) {
+        if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
+        if (c->stage_host[i]) cudaFreeHost(c->stage_host[i]);
+        if (c->stage_stream[i]) cudaStreamDestroy(c->stage_stream[i]);
+        c->stage_dev[i] = nullptr;
+        c->stage_host[i] = nullptr;
+        c->stage_stream[i] = nullptr;
+    }
+    c->stage_ready = false;
+}
+
+int ensure_stage(qt_ctx* c) {
+    if (c->stage_ready) return 0;
+    // 8 MiB per operand per chunk; three workers per four host cores, at most STAGE.  Measured on the
+    // 16-core GPU box (768 MiB per batch): 2 / 4 / 8 / 12 / 16 workers -> 38.8 / 25.4 / 17.5 / 16.3 / 17.4 ms
+    // (driver-staged cudaMemcpyAsync: 61 ms; pinned buffers: 11.3 ms)
+    c->stage_polys = std::max<size_t>(1, (size_t)(2u << 20) / c->p.n);
+    int w = (int)std::thread::hardware_concurrency() * 3 / (4 * std::max(1, c->stage_share));
+    if (const char* e = getenv("QT_STAGE_THREADS")) w = atoi(e);  // tuning aid
+    c->stage_workers = std::min((int)qt_ctx::STAGE, std::max(1, w));
+    const size_t bytes = 2 * c->stage_polys * c->p.n * sizeof(uint32_t);
+    for (int i = 0; i < c->stage_workers; i++) {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stage_stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&c->stage_dev[i], bytes);
+        if (e == cudaSuccess) e = cudaMallocHost(&c->stage_host[i], bytes);
+        if (e != cudaSuccess) {
+            release_stage(c);
+            return (int)e;
+        }
+    }
+    c->stage_ready = true;
+    return 0;
+}
+
+// true when cudaMemcpyAsync from/to p would be staged by the driver (ordinary malloc/new memory)
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 int ensure_pipe(qt_ctx* c) {
     if (c->pipe_ready) return 0;
     // chunk: 4096 polynomials of n=1024 (16 MiB per operand) — large enough for PCIe efficiency,
@@ -371,6 +426,7 @@ int qt_destroy(qt_ctx* c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     release_pipe(c);
+    release_stage(c);
     for (int k = 0; k < 2; k++)
         if (c->d_tab[k]) cudaFree(c->d_tab[k]);
     if (c->d_tab_split) cudaFree(c->d_tab_split);
@@ -500,6 +556,52 @@ int qt_fill_uniform(qt_ctx* c, uint32_t* a, size_t count, uint64_t seed, uint64_
     return (int)cudaGetLastError();
 }
 
+// Pageable operands: cudaMemcpyAsync would fall back to the driver's own single staging path
+// (measured 13 GB/s, 61 ms for the 768 MiB of one n=1024 batch of 65 536).  Instead a few worker threads
+// each take chunks end to end — copy x, y into their pinned buffer, H2D, kernel, D2H, copy z out — so the
+// host-side copies of one worker overlap the transfers and kernels of the others.  Operands that ARE
+// pinned are transferred in place.
+static int staged_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int nuss_ring,
+                           bool px, bool py, bool pz) {
+    int rc0 = ensure_stage(c);
+    if (rc0) return rc0;
+    const size_t n = c->p.n, chunk = c->stage_polys;
+    const size_t nchunks = (B + chunk - 1) / chunk;
+    const int workers = (int)std::min<size_t>((size_t)c->stage_workers, nchunks);
+    std::atomic<size_t> next{0};
+    std::atomic<int> err{0};
+    auto work = [&](int w) {
+        if (cudaSetDevice(c->device) != cudaSuccess) { err = (int)cudaGetLastError(); return; }
+        cudaStream_t s = c->stage_stream[w];
+        uint32_t* dx = c->stage_dev[w];
+        uint32_t* dy = dx + chunk * n;
+        uint32_t* hx = c->stage_host[w];
+        uint32_t* hy = hx + chunk * n;
+        for (size_t i = next++; i < nchunks && !err; i = next++) {
+            const size_t off = i * chunk * n, cnt = std::min(chunk, B - i * chunk), bytes = cnt * n * sizeof(uint32_t);
+            int rc = 0;
+            if (px) memcpy(hx, x + off, bytes);
+            rc = (int)cudaMemcpyAsync(dx, px ? hx : x + off, bytes, cudaMemcpyHostToDevice, s);
+            if (py) memcpy(hy, y + off, bytes);
+            if (!rc) rc = (int)cudaMemcpyAsync(dy, py ? hy : y + off, bytes, cudaMemcpyHostToDevice, s);
+            if (!rc) {
+                if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
+                else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, s); if (!rc) c->launches++; }
+            }
+            if (!rc) rc = (int)cudaMemcpyAsync(pz ? hx : z + off, dx, bytes, cudaMemcpyDeviceToHost, s);
+            const cudaError_t e = cudaStreamSynchronize(s);  // always: nothing of this chunk may stay in flight
+            if (!rc && e != cudaSuccess) rc = (int)e;
+            if (!rc && pz) memcpy(z + off, hx, bytes);
+            if (rc) err = rc;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < workers; w++) th.emplace_back(work, w);
+    work(0);
+    for (auto& t : th) t.join();
+    return err;
+}
+
 // Host-pointer product: chunks of pipe_polys polynomials rotate through PIPE device slots; each
 // slot's stream does H2D(x,y) -> kernel -> D2H(z), so copies of neighbouring chunks overlap with
 // compute and with each other (PCIe is full duplex).
@@ -507,6 +609,8 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
     if (!c || ((!x || !y || !z) && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
     DeviceGuard g(c->device);
+    const bool px = is_pageable(x), py = is_pageable(y), pz = is_pageable(z);
+    if (px || py || pz) return staged_pipeline(c, x, y, z, B, nuss_ring, px, py, pz);
     int rc = ensure_pipe(c);
     if (rc) return rc;
     const size_t n = c->p.n, chunk = c->pipe_polys;
@@ -567,6 +671,11 @@ int qt_polymul_host_multi(int set, const uint32_t* x, const uint32_t* y, uint32_
             if (hi == lo) return;
             int rc = 0;
             if (!g_multi_ctx[set][gidx]) rc = qt_create(set, gidx, &g_multi_ctx[set][gidx]);
+            if (!rc && g_multi_ctx[set][gidx]->stage_share != ngpus) {  // the devices share the host cores
+                DeviceGuard dg(gidx);
+                release_stage(g_multi_ctx[set][gidx]);
+                g_multi_ctx[set][gidx]->stage_share = ngpus;
+            }
             if (!rc) rc = qt_polymul_host(g_multi_ctx[set][gidx], x + lo * p.n, y + lo * p.n, z + lo * p.n, hi - lo);
             rcs[gidx] = rc;
         });

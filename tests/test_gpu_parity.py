@@ -185,15 +185,26 @@ def test_in_place_and_fill_uniform(engines, oracle):
 @pytest.mark.parametrize("s", [0, 1, 3])
 def test_host_pointer_entry_point(engines, oracle, s):
     eng = engines[s]
-    B = 4096 * (1024 // eng.n if eng.n <= 1024 else 1) // 2 + 37  # spans several pipeline chunks? no: one and a bit
     B = (4 << 20) // eng.n * 2 + 37                                 # two full chunks + a ragged tail
     x, y = rand_pair(eng.q, B * eng.n, 77 + s)
     z = eng.polymul_host(x, y)                                      # pageable numpy memory
     idx = np.r_[0:3, B // 2 - 1: B // 2 + 2, B - 3: B]
     pick = lambda a: np.concatenate([a[i * eng.n:(i + 1) * eng.n] for i in idx])
     assert np.array_equal(pick(z), oracle.polymul(s, pick(x), pick(y)))
-    assert np.array_equal(z, eng.polymul_np(x, y))                  # whole batch: host path == device path
+    zd = eng.polymul_np(x, y)
+    assert np.array_equal(z, zd)                                    # whole batch: host path == device path
     assert eng.polymul_host(x[:0], y[:0]).size == 0                  # empty batch
+    # pinned buffers take the in-place copy pipeline; mixed pinned / pageable operands are allowed
+    import torch
+    pin = lambda a: torch.from_numpy(a.view(np.int32)).pin_memory().numpy().view(np.uint32)
+    xp, yp = pin(x), pin(y)
+    zp = pin(np.zeros_like(x))
+    eng.polymul_host(xp, yp, zp)
+    assert np.array_equal(zp, zd)
+    assert np.array_equal(eng.polymul_host(xp, y), zd)              # x pinned, y and z pageable
+    zp[:] = 0
+    eng.polymul_host(x, y, zp)                                      # only z pinned
+    assert np.array_equal(zp, zd)
 
 
 def test_multi_gpu_host_sharding(qt, oracle):
