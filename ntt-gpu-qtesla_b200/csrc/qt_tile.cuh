@@ -134,13 +134,33 @@ template <int SET> struct Tile {
     static QT_HD uint32_t scanon(uint32_t r) { return csub(umin32(r, r + Q), Q); }
 
     // forward (Cooley-Tukey) butterfly: (x, y) -> (x + w y, x - w y)
-    static QT_HD void ct(uint32_t& x, uint32_t& y, TwPair t) {
+    // q = 2^23 + 2^14 + 1 (qTESLA-III): hi*q as two shift-adds (LEA).  Moves one multiply-add of a butterfly
+    // from the multiply pipe (the binding unit) to the ALU at the price of two more issue slots, so it pays
+    // only for a fraction of the butterflies: every QT_SHIFT_MOD-th one (0 = never).  Measured at n=1024,
+    // batch 65 536: never 238.9, every 2nd < 238, 3rd 238.9, 4th 240.9, 5th 240.2, 8th 240.5 M polymul/s.
+    // (Inline PTX: written in C the compiler folds the shifts back into one IMAD.)
+#ifndef QT_SHIFT_MOD
+#define QT_SHIFT_MOD 4
+#endif
+    static constexpr bool SHIFT_Q = (Q == (1u << 23) + (1u << 14) + 1u) && (QT_SHIFT_MOD != 0);
+    static QT_HD void ct(uint32_t& x, uint32_t& y, TwPair t, uint32_t idx = 1) {
         if (LAZY) {
             // 3 multiply-pipe instructions + ONE add: the sum rides on the multiply-add's addend,
             // the difference is 2x - x'
             const uint32_t hi = (uint32_t)mulhi32s(y, t.ws);
             const uint32_t u = y * t.w + x;
-            const uint32_t xn = u - hi * Q;
+            uint32_t xn;
+            if (SHIFT_Q && idx % (QT_SHIFT_MOD ? QT_SHIFT_MOD : 1) == 0) {
+#if defined(__CUDA_ARCH__)
+                uint32_t m;
+                asm("{\n\t.reg .u32 a, b;\n\tshl.b32 a, %1, 14;\n\tadd.u32 a, a, %1;\n\tshl.b32 b, %1, 23;\n\tadd.u32 %0, a, b;\n\t}" : "=r"(m) : "r"(hi));
+#else
+                const uint32_t m = ((hi << 14) + hi) + (hi << 23);
+#endif
+                xn = u - m;
+            } else {
+                xn = u - hi * Q;
+            }
             y = x + x - xn;
             x = xn;
         } else {
@@ -168,7 +188,7 @@ template <int SET> struct Tile {
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {  // flat butterfly index: constant trip count
                 const uint32_t g = i / half, j = i % half;
-                ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>(ub + (1u << l) + g));
+                ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>(ub + (1u << l) + g), i);
             }
         }
     }
@@ -187,7 +207,7 @@ template <int SET> struct Tile {
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t g = i / half, j = i % half;
-                ct(v[2 * g * half + j], v[2 * g * half + j + half], lane_slot(tw, G - G0 + g, BLOCKS));
+                ct(v[2 * g * half + j], v[2 * g * half + j + half], lane_slot(tw, G - G0 + g, BLOCKS), i);
             }
         }
     }
@@ -214,7 +234,7 @@ template <int SET> struct Tile {
                         x = a + b;
                         y = a - b;
                     } else {
-                        ct(x, y, uni_tw<SET, UNI_INV_PLAIN>(l + j));
+                        ct(x, y, uni_tw<SET, UNI_INV_PLAIN>(l + j), i);
                     }
                 }
             }
@@ -245,7 +265,7 @@ template <int SET> struct Tile {
 #pragma unroll
                 for (uint32_t i = 0; i < E / 2; i++) {
                     const uint32_t u = i / G, g = i % G;
-                    ct(v[2 * G * u + g], v[2 * G * u + g + G], lane_slot(p.inv, G - 1 + g, LPP));
+                    ct(v[2 * G * u + g], v[2 * G * u + g + G], lane_slot(p.inv, G - 1 + g, LPP), i);
                 }
             }
 #pragma unroll
