@@ -21,7 +21,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--set", default="III")
 ap.add_argument("--min-log2", type=int, default=10)
 ap.add_argument("--max-log2", type=int, default=22)
-ap.add_argument("--cpu", action="store_true", help="also time the reference CPU path on the host cores (rank 0, 2 s sample)")
 args = ap.parse_args()
 qt = load()
 rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -34,15 +33,6 @@ eng = qt.Engine(set_id, local)
 stream = torch.cuda.Stream(device=dev)
 eng.set_stream(stream.cuda_stream)
 n = eng.n
-cpu_rate = None
-if args.cpu and rank == 0:
-    from oracle_lib import Oracle, Reference
-    o = Oracle()
-    th = len(os.sched_getaffinity(0))
-    cnt = 256 * th
-    xs = o.splitmix(1, 0, eng.q, cnt * n); ys = o.splitmix(2, 0, eng.q, cnt * n)
-    run = (lambda: Reference().polymul(xs, ys, 0, th)) if (Reference.available() and set_id == 1) else (lambda: o.polymul(set_id, xs, ys, threads=th))
-    run(); t0 = time.perf_counter(); run(); cpu_rate = cnt / (time.perf_counter() - t0)
 for lg in range(args.min_log2, args.max_log2 + 1):
     B = 1 << lg
     lo, hi = qt.sharding.shard_bounds(B, rank, world)
@@ -70,9 +60,6 @@ for lg in range(args.min_log2, args.max_log2 + 1):
         line = {"param_set": args.set, "n": n, "total_batch": B, "n_gpus": world, "per_gpu_batch": b, "steps": steps,
                 "us_per_step": ms / steps * 1e3, "polymuls_per_s": B * steps / (ms * 1e-3),
                 "working_set_MiB": 3 * b * n * 4 / 2 ** 20}
-        if cpu_rate:
-            line["cpu_reference_polymuls_per_s"] = cpu_rate
-            line["cpu_threads"] = len(os.sched_getaffinity(0))
         os.write(_OUT, (json.dumps(line) + "\n").encode())
     del x, y, z
 eng.close()
