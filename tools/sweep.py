@@ -9,7 +9,6 @@ resident, CUDA events, max over ranks.  One JSON line per batch size on rank 0.
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import torch.distributed as dist
