@@ -175,6 +175,8 @@ int upload_tables(qt_ctx* c) {
     }
 }
 
+// (TMA kernels: grid = min(#SMs, tiles) — with the SM-interleaved tile order a small batch spreads over all
+//  SMs, a few warps each, instead of filling 16 warps of a few SMs: B=1024 at n=1024 takes 7 warps on 148 SMs.)
 inline int grid_for(int max_grid, size_t tiles) {
     size_t ctas = (tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     return (int)std::max<size_t>(1, std::min<size_t>((size_t)max_grid, ctas));
@@ -186,10 +188,10 @@ template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32
     const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;  // bulk copies need 16-byte alignment
     const bool tma = c->occ_tma > 0 && aligned && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
     if (SET == SET_P_III && c->split_ok && aligned && (c->variant == 3 || c->variant == 0))
-        k_polymul_split<0><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (B + SplitShape::WARPS - 1) / SplitShape::WARPS)),
+        k_polymul_split<0><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B)),
                           SplitShape::WARPS * 32, SplitShape::SMEM, s>>>(x, y, z, B, c->d_tab_split);
     else if (tma)
-        k_polymul_tma<SET><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS)),
+        k_polymul_tma<SET><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, tiles)),
                              TmaCfg<SET>::WARPS * 32, c->smem_tma, s>>>(
             x, y, z, B, c->d_tab[1]);
     else
@@ -203,13 +205,13 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
     if (c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
     if ((((uintptr_t)ahat | (uintptr_t)y) & 15) != 0) return QT_ERR_BAD_ARG;  // 128-bit / bulk-copy alignment
     if (SET == SET_P_III && c->split_ok && c->variant != 2) {
-        const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (B + SplitShape::WARPS - 1) / SplitShape::WARPS));
+        const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B));
         if (bcast) k_polymul_split<1><<<g, SplitShape::WARPS * 32, SplitShape::SMEM_BCAST, c->stream>>>(ahat, y, z, B, c->d_tab_split);
         else k_polymul_split<2><<<g, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream>>>(ahat, y, z, B, c->d_tab_split);
         c->launches++;
         return (int)cudaGetLastError();
     }
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS));
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
     if (bcast) k_polymul_ntt<SET, true><<<grid, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM_BCAST, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
     else k_polymul_ntt<SET, false><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
     c->launches++;
@@ -217,7 +219,7 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
 }
 template <int SET, bool INV> int launch_ntt_tma(qt_ctx* c, uint32_t* a, size_t B) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (tiles + TmaCfg<SET>::WARPS - 1) / TmaCfg<SET>::WARPS));
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
     k_ntt_tma<SET, INV><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(a, B, c->d_tab[0]);
     c->launches++;
     return (int)cudaGetLastError();

@@ -567,8 +567,7 @@ int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z,
     if constexpr (K::R == 32) {
         if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15) != 0) return -2;  // 128-bit accesses
         using W0 = NussWarp<SET, 0>;
-        const size_t ctas = (batch + W0::WARPS - 1) / W0::WARPS;
-        const int g = (int)(ctas < (size_t)max_grid ? ctas : (size_t)max_grid);
+        const int g = (int)(batch < (size_t)max_grid ? batch : (size_t)max_grid);  // small batches spread over all SMs
         if (ring == 0) k_nussbaumer_warp<SET, 0><<<g, W0::WARPS * 32, W0::SMEM_BYTES, s>>>(x, y, z, batch);
         else k_nussbaumer_warp<SET, 1><<<g, NussWarp<SET, 1>::WARPS * 32, NussWarp<SET, 1>::SMEM_BYTES, s>>>(x, y, z, batch);
         return (int)cudaGetLastError();
