@@ -404,15 +404,26 @@ template <int SET, int RING> struct NussWarp {
 #pragma unroll
         for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
         if (RING == 0) {
+            // naive (NTT.cu:147-165) keeps two chains per output, A over j <= k and B over j > k, folding
+            // after every term.  A chain's final value is a function of the INTEGER sum T of its products
+            // only: it is congruent to T, lies in [0, 2^32-1], and is 0 exactly when T = 0 (a fold of a
+            // non-zero value is never 0).  So each chain is summed exactly in three 32-bit limbs (one
+            // multiply-add-with-carry per term) and folded once with the same end-around-carry adds — bit for
+            // bit the reference's result, including which representation of zero comes out.
 #pragma unroll
-            for (uint32_t k = 0; k < 32; k++) {  // naive, NTT.cu:147-165: chains A (j<=k) and B (j>k)
-                uint32_t A = NussOps<SET, 0>::fold((uint64_t)x[0] * y[k]), B = 0;
+            for (uint32_t k = 0; k < 32; k++) {
+                uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
 #pragma unroll
-                for (uint32_t j = 1; j < 32; j++) {
-                    if (j <= k) A = NussOps<SET, 0>::fold((uint64_t)x[j] * y[(k - j) & 31] + A);
-                    else B = NussOps<SET, 0>::fold((uint64_t)x[j] * y[(32 + k - j) & 31] + B);
+                for (uint32_t j = 0; j < 32; j++) {
+                    if (j <= k)
+                        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                            : "+r"(a0), "+r"(a1), "+r"(a2) : "r"(x[j]), "r"(y[(k - j) & 31]));
+                    else
+                        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                            : "+r"(b0), "+r"(b1), "+r"(b2) : "r"(x[j]), "r"(y[(32 + k - j) & 31]));
                 }
-                xr[k] = NussOps<SET, 0>::sub(A, B);
+                using O0 = NussOps<SET, 0>;
+                xr[k] = O0::sub(O0::add(O0::add(a0, a1), a2), O0::add(O0::add(b0, b1), b2));
             }
         } else if (LAZYQ) {
             // 2^32 (the Montgomery factor) times 2^-(LOGM+1) (every halving of the inverse stages), signed Shoup form

@@ -264,6 +264,11 @@ def test_nussbaumer_ring_equals_oracle(engines, oracle, qt):
     x[:1024] = 1; y[:1024] = 1                                       # the reference's all-ones fixture
     x[1024:2048] = 0xFFFFFFFF                                        # non-normalised zeros
     y[2048:3072] = 0; y[2048 + rng.choice(1024, 40, replace=False)] = 0xFFFFFFFE   # sparse ternary (-1)
+    # products that are multiples of 2^32-1 without being zero (the chain must answer 0xFFFFFFFF, not 0),
+    # and products whose 64-bit sum overflows
+    x[3072:4096] = 0; y[3072:4096] = 0
+    x[3072] = 3; y[3072] = 0x55555555; x[3073] = 0x10000; y[3073] = 0x10000; x[3074] = 0xFFFFFFFF; y[3074] = 0xFFFFFFFF
+    x[4096:5120] = 0xFFFFFFFE; y[4096:5120] = 0xFFFFFFFE
     tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda(); tz = torch.empty_like(tx)
     try:
         eng.nussbaumer(tx, ty, tz, qt.RING_2P32M1)
