@@ -548,7 +548,7 @@ k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
 template <int SET, bool INVERSE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_ntt_natural(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
-    using T = Tile<SET>;
+    using T = Tile<SET, !INVERSE>;
     using S = KernelShape<SET>;
     extern __shared__ uint4 smem_raw[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);

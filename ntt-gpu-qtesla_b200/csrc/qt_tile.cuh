@@ -77,7 +77,9 @@ QT_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 struct alignas(16) U4 { uint32_t x, y, z, w; };  // 128-bit shared-memory access unit
 
-template <int SET> struct Tile {
+// SHIFT_OK = false switches the shift-add form of hi*q off (see ct(); it costs the natural-order inverse
+// kernel 12 % while every other kernel gains or is unaffected).
+template <int SET, bool SHIFT_OK = true> struct Tile {
     using C = Cfg<SET>;
     static constexpr uint32_t N = C::N, Q = C::Q, LOGN = C::LOGN, E = C::E, LOGE = C::LOGE;
     static constexpr uint32_t PPW = C::PPW, LPP = C::LPP, LB1 = C::LB1, LB2 = C::LB2;
@@ -142,7 +144,7 @@ template <int SET> struct Tile {
 #ifndef QT_SHIFT_MOD
 #define QT_SHIFT_MOD 4
 #endif
-    static constexpr bool SHIFT_Q = (Q == (1u << 23) + (1u << 14) + 1u) && (QT_SHIFT_MOD != 0);
+    static constexpr bool SHIFT_Q = SHIFT_OK && (Q == (1u << 23) + (1u << 14) + 1u) && (QT_SHIFT_MOD != 0);
     static QT_HD void ct(uint32_t& x, uint32_t& y, TwPair t, uint32_t idx = 1) {
         if (LAZY) {
             // 3 multiply-pipe instructions + ONE add: the sum rides on the multiply-add's addend,

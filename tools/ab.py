@@ -57,6 +57,7 @@ for name in args.sets.split(","):
         print(f"{name:6s} cached: {ex}")
     w = x.clone()
     for nm, fn in (("ntt_forward", lambda: eng.ntt_forward(w, B)), ("ntt_inverse", lambda: eng.ntt_inverse(w, B)),
+                   ("fwd_natural", lambda: eng.ntt_forward_natural(w, B)), ("inv_natural", lambda: eng.ntt_inverse_natural(w, B)),
                    ("pointwise", lambda: eng.pointwise(x, y, z, B)), ("bitrev_copy", lambda: eng.bitrev_copy(x, z, B))):
         r = timeit(fn, args.steps)
         print(f"{name:6s} {nm:12s}: {r/1e6:8.2f} M poly/s  ({r*eng.n*8/1e9:7.1f} GB/s r+w)", flush=True)
