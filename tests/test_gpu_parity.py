@@ -207,6 +207,35 @@ def test_host_pointer_entry_point(engines, oracle, s):
     assert np.array_equal(zp, zd)
 
 
+def test_context_lifecycle_and_small_host_batches(qt, oracle):
+    """Contexts can be created and destroyed repeatedly (tables, streams, pipelines are released), several
+    contexts of different sets share a device, and the host entry points handle batches around the chunk
+    size of both pipelines (pinned: 4 Mi words per chunk, pageable: 2 Mi words)."""
+    import torch
+    free0 = torch.cuda.mem_get_info()[0]
+    for rep in range(6):
+        es = [qt.Engine(s, 0) for s in ALL_SETS]
+        for s, e in zip(ALL_SETS, es):
+            x, y = rand_pair(e.q, 3 * e.n, 1000 + rep * 10 + s)
+            assert np.array_equal(e.polymul_host(x, y), oracle.polymul(s, x, y))   # builds the staged pipeline
+        for e in es:
+            e.close()
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20), "device memory leaked by create/destroy"
+    eng = qt.Engine(1, 0)
+    n = eng.n
+    chunk = (2 << 20) // n
+    pin = lambda a: torch.from_numpy(a.view(np.int32)).pin_memory().numpy().view(np.uint32)
+    for B in (1, 2, chunk - 1, chunk, chunk + 1, 2 * chunk + 1):
+        x, y = rand_pair(eng.q, B * n, 2000 + B)
+        ref = eng.polymul_np(x, y)
+        assert np.array_equal(eng.polymul_host(x, y), ref), B                       # pageable
+        zp = pin(np.zeros_like(x))
+        eng.polymul_host(pin(x), pin(y), zp)                                        # pinned
+        assert np.array_equal(zp, ref), B
+    eng.close()
+
+
 def test_multi_gpu_host_sharding(qt, oracle):
     # contiguous batch slices over however many GPUs the box has (1 is fine): no collective involved
     B = 301
