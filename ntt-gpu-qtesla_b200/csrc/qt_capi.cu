@@ -290,17 +290,22 @@ void release_stage(qt_ctx* c) {
     c->stage_ready = false;
 }
 
-int ensure_stage(qt_ctx* c) {
-    if (c->stage_ready) return 0;
-    // 8 MiB per operand per chunk; three workers per four host cores, at most STAGE.  Measured on the
-    // 16-core GPU box (768 MiB per batch): 2 / 4 / 8 / 12 / 16 workers -> 38.8 / 25.4 / 17.5 / 16.3 / 17.4 ms
-    // (driver-staged cudaMemcpyAsync: 61 ms; pinned buffers: 11.3 ms)
-    c->stage_polys = std::max<size_t>(1, (size_t)(2u << 20) / c->p.n);
-    int w = (int)std::thread::hardware_concurrency() * 3 / (4 * std::max(1, c->stage_share));
-    if (const char* e = getenv("QT_STAGE_THREADS")) w = atoi(e);  // tuning aid
-    c->stage_workers = std::min((int)qt_ctx::STAGE, std::max(1, w));
+// creates the staging resources of workers [0, want) that do not exist yet (small batches need few)
+int ensure_stage(qt_ctx* c, size_t polys) {
+    if (!c->stage_ready) {
+        // 8 MiB per operand per chunk; three workers per four host cores, at most STAGE.  Measured on the
+        // 16-core GPU box (768 MiB per batch): 2 / 4 / 8 / 12 / 16 workers -> 38.8 / 25.4 / 17.5 / 16.3 / 17.4 ms
+        // (driver-staged cudaMemcpyAsync: 61 ms; pinned buffers: 11.3 ms)
+        c->stage_polys = std::max<size_t>(1, (size_t)(2u << 20) / c->p.n);
+        int w = (int)std::thread::hardware_concurrency() * 3 / (4 * std::max(1, c->stage_share));
+        if (const char* e = getenv("QT_STAGE_THREADS")) w = atoi(e);  // tuning aid
+        c->stage_workers = std::min((int)qt_ctx::STAGE, std::max(1, w));
+        c->stage_ready = true;
+    }
     const size_t bytes = 2 * c->stage_polys * c->p.n * sizeof(uint32_t);
-    for (int i = 0; i < c->stage_workers; i++) {
+    const size_t want = std::min<size_t>((size_t)c->stage_workers, (polys + c->stage_polys - 1) / c->stage_polys);
+    for (size_t i = 0; i < want; i++) {
+        if (c->stage_host[i]) continue;
         cudaError_t e = cudaStreamCreateWithFlags(&c->stage_stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&c->stage_dev[i], bytes);
         if (e == cudaSuccess) e = cudaMallocHost(&c->stage_host[i], bytes);
@@ -309,7 +314,6 @@ int ensure_stage(qt_ctx* c) {
             return (int)e;
         }
     }
-    c->stage_ready = true;
     return 0;
 }
 
@@ -565,7 +569,7 @@ int qt_fill_uniform(qt_ctx* c, uint32_t* a, size_t count, uint64_t seed, uint64_
 // pinned are transferred in place.
 static int staged_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int nuss_ring,
                            bool px, bool py, bool pz) {
-    int rc0 = ensure_stage(c);
+    int rc0 = ensure_stage(c, B);
     if (rc0) return rc0;
     const size_t n = c->p.n, chunk = c->stage_polys;
     const size_t nchunks = (B + chunk - 1) / chunk;
