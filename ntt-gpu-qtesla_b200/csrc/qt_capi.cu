@@ -290,8 +290,8 @@ void release_stage(qt_ctx* c) {
     c->stage_ready = false;
 }
 
-// creates the staging resources of workers [0, want) that do not exist yet (small batches need few)
-int ensure_stage(qt_ctx* c, size_t polys) {
+// decides the worker count (once) and creates the staging resources of workers [0, want) that do not exist yet
+int ensure_stage(qt_ctx* c, size_t want) {
     if (!c->stage_ready) {
         // 8 MiB per operand per chunk; three workers per four host cores, at most STAGE.  Measured on the
         // 16-core GPU box (768 MiB per batch): 2 / 4 / 8 / 12 / 16 workers -> 38.8 / 25.4 / 17.5 / 16.3 / 17.4 ms
@@ -303,8 +303,7 @@ int ensure_stage(qt_ctx* c, size_t polys) {
         c->stage_ready = true;
     }
     const size_t bytes = 2 * c->stage_polys * c->p.n * sizeof(uint32_t);
-    const size_t want = std::min<size_t>((size_t)c->stage_workers, (polys + c->stage_polys - 1) / c->stage_polys);
-    for (size_t i = 0; i < want; i++) {
+    for (size_t i = 0; i < std::min<size_t>(want, (size_t)c->stage_workers); i++) {
         if (c->stage_host[i]) continue;
         cudaError_t e = cudaStreamCreateWithFlags(&c->stage_stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&c->stage_dev[i], bytes);
@@ -569,20 +568,26 @@ int qt_fill_uniform(qt_ctx* c, uint32_t* a, size_t count, uint64_t seed, uint64_
 // pinned are transferred in place.
 static int staged_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int nuss_ring,
                            bool px, bool py, bool pz) {
-    int rc0 = ensure_stage(c, B);
+    int rc0 = ensure_stage(c, 0);  // decides the worker count
     if (rc0) return rc0;
-    const size_t n = c->p.n, chunk = c->stage_polys;
+    // chunk: at most the staging buffer; smaller for small batches so that every worker gets ~2 chunks
+    // (overlap), but not below 1 MiB per operand (a worker thread costs ~50 us to start)
+    const size_t n = c->p.n, cap = c->stage_polys;
+    const size_t chunk = std::min(cap, std::max<size_t>(std::max<size_t>(1, (256u << 10) / n),
+                                                         (B + 2 * c->stage_workers - 1) / (2 * c->stage_workers)));
     const size_t nchunks = (B + chunk - 1) / chunk;
     const int workers = (int)std::min<size_t>((size_t)c->stage_workers, nchunks);
+    rc0 = ensure_stage(c, (size_t)workers);
+    if (rc0) return rc0;
     std::atomic<size_t> next{0};
     std::atomic<int> err{0};
     auto work = [&](int w) {
         if (cudaSetDevice(c->device) != cudaSuccess) { err = (int)cudaGetLastError(); return; }
         cudaStream_t s = c->stage_stream[w];
         uint32_t* dx = c->stage_dev[w];
-        uint32_t* dy = dx + chunk * n;
+        uint32_t* dy = dx + cap * n;
         uint32_t* hx = c->stage_host[w];
-        uint32_t* hy = hx + chunk * n;
+        uint32_t* hy = hx + cap * n;
         for (size_t i = next++; i < nchunks && !err; i = next++) {
             const size_t off = i * chunk * n, cnt = std::min(chunk, B - i * chunk), bytes = cnt * n * sizeof(uint32_t);
             int rc = 0;
@@ -619,7 +624,10 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
     if (px || py || pz) return staged_pipeline(c, x, y, z, B, nuss_ring, px, py, pz);
     int rc = ensure_pipe(c);
     if (rc) return rc;
-    const size_t n = c->p.n, chunk = c->pipe_polys;
+    const size_t n = c->p.n, cap = c->pipe_polys;
+    // smaller chunks for small batches (about two per slot) so that H2D, kernel and D2H still overlap
+    const size_t chunk = std::min(cap, std::max<size_t>(std::max<size_t>(1, (128u << 10) / n),
+                                                         (B + 2 * c->pipe_slots - 1) / (2 * c->pipe_slots)));
     size_t done = 0;
     int slot = 0;
     while (done < B && !rc) {
@@ -627,7 +635,7 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
         const size_t bytes = cnt * n * sizeof(uint32_t);
         cudaStream_t s = c->pipe_stream[slot];
         uint32_t* dx = c->pipe_buf[slot];
-        uint32_t* dy = dx + chunk * n;
+        uint32_t* dy = dx + cap * n;
         rc = (int)cudaMemcpyAsync(dx, x + done * n, bytes, cudaMemcpyHostToDevice, s);
         if (!rc) rc = (int)cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s);
         if (!rc) {
