@@ -383,13 +383,48 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
         for (uint32_t r = 0; r < E; r++)
             if (valid) g_tile[nat_off(lane, r)] = v[r];
     }
-    static QT_HD void sts_rows(const uint32_t (&v)[E], uint32_t* buf, uint32_t lane) {
+    // swz(row_off(lane, r)) as (one of 8 per-lane bases) + (compile-time offset), for the two-polynomials-per-
+    // warp tile.  With one polynomial per warp the compiler finds this form by itself (the XORed bits come from
+    // the lane term only); here bit 4 mixes r with the run-time polynomial index p = lane / LPP:
+    //   (p N + l + 16 r) ^ (c << 2) ^ (p << 4),  c = (r >> 1) & 7 = clo + 4 chi,  b = (r & 1) ^ chi
+    //   = [p N + (l ^ (clo << 2)) + (b ? -16 p : +16 p)] + 16 b + 16 (r & ~1)
+    // which saves ~2 address instructions on each of the 96 row accesses of a product.
+    struct RowBases { uint32_t b[4][2]; };
+    static QT_HD RowBases row_bases(uint32_t lane) {
+        static_assert(PPW != 2 || (N == 512 && LPP == 16 && LOGE == 5), "row_bases is written for n = 512");
+        RowBases B;
+        const uint32_t p = lane / LPP, l = lane % LPP;
 #pragma unroll
-        for (uint32_t r = 0; r < E; r++) buf[swz(row_off(lane, r))] = v[r];
+        for (uint32_t clo = 0; clo < 4; clo++) {
+            const uint32_t L = p * N + (l ^ (clo << 2));
+            B.b[clo][0] = L + 16 * p;
+            B.b[clo][1] = L - 16 * p;
+        }
+        return B;
+    }
+    static QT_HD uint32_t rows_addr(const RowBases& B, uint32_t r) {
+        const uint32_t c = (r >> 1) & 7u, bit = (r & 1u) ^ (c >> 2);
+        return B.b[c & 3u][bit] + 16 * bit + 16 * (r & ~1u);
+    }
+    static QT_HD void sts_rows(const uint32_t (&v)[E], uint32_t* buf, uint32_t lane) {
+        if (PPW == 2) {
+            const RowBases B = row_bases(lane);
+#pragma unroll
+            for (uint32_t r = 0; r < E; r++) buf[rows_addr(B, r)] = v[r];
+        } else {
+#pragma unroll
+            for (uint32_t r = 0; r < E; r++) buf[swz(row_off(lane, r))] = v[r];
+        }
     }
     static QT_HD void lds_rows(uint32_t (&v)[E], const uint32_t* buf, uint32_t lane) {
+        if (PPW == 2) {
+            const RowBases B = row_bases(lane);
 #pragma unroll
-        for (uint32_t r = 0; r < E; r++) v[r] = buf[swz(row_off(lane, r))];
+            for (uint32_t r = 0; r < E; r++) v[r] = buf[rows_addr(B, r)];
+        } else {
+#pragma unroll
+            for (uint32_t r = 0; r < E; r++) v[r] = buf[swz(row_off(lane, r))];
+        }
     }
     static QT_HD void sts_cols(const uint32_t (&v)[E], uint32_t* buf, uint32_t lane) {
 #pragma unroll

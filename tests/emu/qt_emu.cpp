@@ -175,6 +175,13 @@ template <int SET> struct Emu {
                 }
                 for (int b = 0; b < 32; b++) worst = cnt[b] > worst ? cnt[b] : worst;
             }
+        // the base + offset form of the rows addresses (two polynomials per warp) must equal the swizzle
+        if (T::PPW == 2)
+            for (uint32_t l = 0; l < 32; l++) {
+                const typename T::RowBases B = T::row_bases(l);
+                for (uint32_t r = 0; r < E; r++)
+                    if (T::rows_addr(B, r) != T::swz(T::row_off(l, r))) return -3;
+            }
         // the swizzle must be a permutation of the tile
         std::vector<uint8_t> seen(T::C::TILE_WORDS, 0);
         for (uint32_t o = 0; o < T::C::TILE_WORDS; o++) {
