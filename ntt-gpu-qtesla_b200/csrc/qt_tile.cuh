@@ -335,11 +335,24 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
         return LAZY ? smul_mont(a, b_canonical) : mul_mont(csub(a, TWO_Q), b_canonical);
     }
 
-    // forward output -> canonical [0,q) (only the unfused forward entry point needs it)
+    // forward output -> canonical [0,q) (only the unfused forward entry points need it).
+    // LAZY: |v| < (1 + 1.5 log2 n) q and q = 2^QS + d with a small d, so k = round(v / 2^QS) is within the
+    // stated bound of round(v / q): r = v - k q satisfies |r| <= 2^(QS-1) + |k| d < q and one conditional add
+    // finishes — 1 multiply-pipe instruction per coefficient instead of the 3 of a Shoup reduction.
+    static constexpr uint32_t QS = C::QBITS - 1;                                      // floor(log2 q)
+    static constexpr uint64_t KMAX = ((2 + 3 * (uint64_t)LOGN) * Q >> (QS + 1)) + 2;  // |k| bound
+    static_assert(!LAZY || ((1ull << (QS - 1)) + KMAX * (Q - (1u << QS)) < Q), "canon_fwd: shift-based quotient");
     static QT_HD void canon_fwd(uint32_t (&v)[E]) {
 #pragma unroll
-        for (uint32_t r = 0; r < E; r++)
-            v[r] = LAZY ? scanon(smul_shoup(v[r], TwPair{1u, C::MU32})) : csub(csub(v[r], TWO_Q), Q);
+        for (uint32_t r = 0; r < E; r++) {
+            if (LAZY) {
+                const int32_t k = ((int32_t)v[r] + (int32_t)(1u << (QS - 1))) >> QS;
+                const uint32_t t = v[r] - (uint32_t)k * Q;
+                v[r] = umin32(t, t + Q);
+            } else {
+                v[r] = csub(csub(v[r], TWO_Q), Q);
+            }
+        }
     }
 
     // ---- data movement ----------------------------------------------------------------------------
