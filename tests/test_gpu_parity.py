@@ -51,6 +51,32 @@ def test_fused_polymul_equals_oracle(engines, oracle, s, B, variant):
         eng.set_fused_variant(0)
 
 
+def test_fuzz_batches_sets_variants(engines, oracle):
+    """Random (set, batch, data path) combinations: ragged batches around the grid sizes (148 SMs x 12/16
+    warps, two polynomials per warp for n=512) through fused, cached-transform and unfused entry points."""
+    import torch
+    rng = np.random.default_rng(20261018)
+    special = [147, 148, 149, 295, 296, 297, 2367, 2368, 2369, 1775, 1776, 1777, 4735, 4737]
+    for it in range(36):
+        s = int(rng.integers(0, 4))
+        eng = engines[s]
+        B = int(special[it % len(special)] if it % 3 == 0 else rng.integers(1, 3000))
+        variant = int(rng.choice([0, 1, 2] + ([3] if s == 3 else [])))
+        eng.set_fused_variant(variant)
+        try:
+            x, y = rand_pair(eng.q, B * eng.n, 5000 + it)
+            ref = oracle.polymul(s, x, y, threads=0)
+            assert np.array_equal(eng.polymul_np(x, y), ref), (s, B, variant)
+            tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda(); tz = torch.empty_like(tx)
+            eng.ntt_forward(tx)
+            eng.polymul_ntt(tx, ty, tz, broadcast=False)
+            eng.synchronize()
+            assert np.array_equal(tz.cpu().numpy().view(np.uint32), ref), ("cached", s, B, variant)
+            assert np.array_equal(eng.inverse_natural_np(eng.pointwise_np(eng.forward_natural_np(x), eng.forward_natural_np(y))), ref)
+        finally:
+            eng.set_fused_variant(0)
+
+
 @pytest.mark.parametrize("s", ALL_SETS)
 def test_fused_variants_agree_at_full_size(engines, s):
     import torch
