@@ -162,6 +162,8 @@ int upload_tables(qt_ctx* c) {
         if (cudaFuncSetAttribute(k_polymul_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM) == cudaSuccess &&
             cudaFuncSetAttribute(k_polymul_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM_BCAST) == cudaSuccess &&
             cudaFuncSetAttribute(k_polymul_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM) == cudaSuccess &&
+            cudaFuncSetAttribute(k_ntt_split<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM) == cudaSuccess &&
+            cudaFuncSetAttribute(k_ntt_split<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitShape::SMEM) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polymul_split<0>, SplitShape::WARPS * 32, SplitShape::SMEM) == cudaSuccess)
             c->split_ok = occ > 0;
         else
@@ -224,7 +226,15 @@ template <int SET, bool INV> int launch_ntt_tma(qt_ctx* c, uint32_t* a, size_t B
     c->launches++;
     return (int)cudaGetLastError();
 }
+template <bool INV> int launch_ntt_split(qt_ctx* c, uint32_t* a, size_t B) {
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, B));
+    k_ntt_split<INV><<<grid, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream>>>(a, B, c->d_tab_split);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
 template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
+    if (SET == SET_P_III && c->split_ok && (c->variant == 0 || c->variant == 3) && ((uintptr_t)a & 15) == 0)
+        return launch_ntt_split<false>(c, a, B);
     if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, false>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     k_ntt_forward<SET><<<grid_for(c->grid_fwd, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_tab[0]);
@@ -232,6 +242,8 @@ template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
     return (int)cudaGetLastError();
 }
 template <int SET> int launch_inverse(qt_ctx* c, uint32_t* a, size_t B) {
+    if (SET == SET_P_III && c->split_ok && (c->variant == 0 || c->variant == 3) && ((uintptr_t)a & 15) == 0)
+        return launch_ntt_split<true>(c, a, B);
     if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, true>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     k_ntt_inverse<SET><<<grid_for(c->grid_inv, tiles), WARPS_PER_CTA * 32, c->smem_one, c->stream>>>(a, B, c->d_tab[0]);

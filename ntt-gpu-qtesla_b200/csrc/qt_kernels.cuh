@@ -381,6 +381,102 @@ k_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
     }
 }
 
+// Single transform for n = 2048 on the split tile (qt_ntt_forward / qt_ntt_inverse of qTESLA-p-III), in
+// place, NTT domain in bit-reversed order.  Two one-polynomial buffers per warp alternate between staging
+// of the next tile and scratch of the current one, as in k_ntt_tma.
+template <bool INVERSE>
+__global__ void __launch_bounds__(SplitShape::WARPS * 32, 1)
+k_ntt_split(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
+    using T = SplitShape::T;
+    using G = SplitShape;
+    extern __shared__ uint4 smem_raw[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
+    constexpr int NW = G::WARPS;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* buf0 = s_stage + warp * 2 * G::WORDS;
+    uint64_t* bar0 = s_bar + 2 * warp;
+    const size_t stride = (size_t)gridDim.x * NW;
+    size_t tile = (size_t)warp * gridDim.x + blockIdx.x;
+    auto issue = [&](uint32_t* st, uint64_t* bar, size_t t) {
+        mbar_expect_tx(bar, G::WORDS * (uint32_t)sizeof(uint32_t));
+        bulk_g2s(st, a + t * G::WORDS, G::WORDS * (uint32_t)sizeof(uint32_t), bar);
+    };
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        if (tile < batch) issue(buf0, bar0, tile);
+    }
+    copy_table_to_smem(s_tw, g_lane, T::TABLE_QUADS);
+    __syncthreads();
+    for (uint32_t k = 0; tile < batch; tile += stride, k++) {
+        uint32_t* st = buf0 + (k & 1) * G::WORDS;
+        // the other buffer was released (fence + __syncwarp) at the end of the previous tile
+        if (tile + stride < batch && lane == 0) issue(buf0 + ((k & 1) ^ 1) * G::WORDS, bar0 + ((k & 1) ^ 1), tile + stride);
+        mbar_wait(bar0 + (k & 1), (k >> 1) & 1);
+        uint32_t* gt = a + tile * G::WORDS;
+        uint32_t v[T::E];
+        if (!INVERSE) {
+            {
+                uint32_t hi[T::E];
+#pragma unroll
+                for (uint32_t r = 0; r < T::E; r++) {
+                    v[r] = st[lane + 32 * r];
+                    hi[r] = st[G::HALF + lane + 32 * r];
+                }
+                __syncwarp();
+                T::split_fwd(v, hi);
+                T::sts_rows(hi, st + G::HALF, lane);
+            }
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; h++) {
+                uint32_t* sh = st + h * G::HALF;
+                if (h) T::lds_rows(v, sh, lane);
+                T::fwd_rows(v, 32 * h);
+                T::sts_rows(v, sh, lane);
+                __syncwarp();
+                T::lds_cols(v, sh, lane);
+                T::fwd_cols(v, s_tw + h * T::TW_QUADS + lane);
+                T::canon_fwd(v);
+                T::sts_cols(v, sh, lane);  // re-layout only, so that the global store is coalesced
+                __syncwarp();
+                T::lds_rows(v, sh, lane);
+#pragma unroll
+                for (uint32_t r = 0; r < T::E; r++) gt[h * G::HALF + lane + 32 * r] = v[r];
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; h++) {
+                uint32_t* sh = st + h * G::HALF;
+#pragma unroll
+                for (uint32_t r = 0; r < T::E; r++) v[r] = sh[lane + 32 * r];
+                __syncwarp();              // the unswizzled staging words of this half are all read
+                T::sts_rows(v, sh, lane);  // NTT-domain data is consumed in the cols layout
+                __syncwarp();
+                T::lds_cols(v, sh, lane);
+                T::inv_cols(v, s_tw + (1 - h) * T::TW_QUADS + (T::BLOCKS - 1 - lane));
+                T::sts_cols(v, sh, lane);
+                __syncwarp();
+                T::lds_rows(v, sh, lane);
+                T::template inv_rows<UNI_INV_PLAIN>(v, typename T::LanePtrs{nullptr, nullptr, nullptr}, 32 * h);
+                if (h == 0) T::sts_rows(v, sh, lane);  // parked in this lane's own slots
+            }
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) {
+                uint32_t lo = st[T::swz(T::row_off(lane, r))];
+                T::template split_inv<UNI_INV_PLAIN>(lo, v[r]);
+                gt[lane + 32 * r] = lo;
+                gt[G::HALF + lane + 32 * r] = v[r];
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();  // this buffer is free for the tile after next
+    }
+}
+
 // z = a*y with NTT(a) supplied by the caller (qTESLA's own use: one public polynomial a, transformed
 // once, multiplied by many secrets / sparse challenges).  Two transforms instead of three.
 // a_hat is in the NTT domain exactly as qt_ntt_forward leaves it (canonical, bit-reversed order);
