@@ -287,10 +287,11 @@ def main():
     peaks, peaks_src = load_peaks()
     stream = torch.cuda.Stream(device=dev)
 
-    def run_config(set_id, batch, steps, warmup, sampler=None, variant=None, nuss_ring=None):
+    def run_config(set_id, batch, steps, warmup, sampler=None, variant=None, nuss_ring=None, nuss_variant=0):
         eng = qt.Engine(set_id, local_rank)
         eng.set_stream(stream.cuda_stream)
         eng.set_fused_variant(args.variant if variant is None else variant)
+        eng.set_nussbaumer_variant(nuss_variant)
         step = (lambda: eng.polymul(x, y, z, batch)) if nuss_ring is None else (lambda: eng.nussbaumer(x, y, z, nuss_ring, batch))
         p = eng.params
         words = batch * p.n
@@ -412,6 +413,8 @@ def main():
         st = max(3, min(args.steps, 50))
         variants = {}
         for vname, v in (("direct_loads", 1), ("tma_staged", 2), ("split_tile_n2048", 3)):
+            if v == 3 and p.n != 2048:
+                continue  # the split tile exists for n = 2048 only
             try:
                 e2, _, ms2, _ = run_config(set_id, batch, st, 3, variant=v)
                 variants[vname] = batch * st / (ms2 * 1e-3)
@@ -419,9 +422,11 @@ def main():
             except Exception as ex:  # e.g. variant unsupported for this shape
                 variants[vname] = str(ex)
         nuss = {}
-        for rname, ring in (("ring_2p32m1", qt.RING_2P32M1), ("mod_q", qt.RING_MODQ)):
+        # Z_q row products: schoolbook (the reference's structure) and recursive (split once more); "mod_q" = automatic
+        for rname, ring, nv in (("ring_2p32m1", qt.RING_2P32M1, 0), ("mod_q", qt.RING_MODQ, 0),
+                                ("mod_q_schoolbook_rows", qt.RING_MODQ, 1), ("mod_q_recursive_rows", qt.RING_MODQ, 2)):
             try:
-                e2, _, ms2, _ = run_config(set_id, batch, max(3, min(args.steps, 10)), 3, nuss_ring=ring)
+                e2, _, ms2, _ = run_config(set_id, batch, max(3, min(args.steps, 10)), 3, nuss_ring=ring, nuss_variant=nv)
                 nuss[rname] = batch * max(3, min(args.steps, 10)) / (ms2 * 1e-3)
                 e2.close()
             except Exception as ex:

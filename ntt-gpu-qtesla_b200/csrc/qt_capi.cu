@@ -48,6 +48,7 @@ struct qt_ctx {
     TwQuad* d_tab_split = nullptr;          // n=2048 only: tables of the split tile (k_polymul_split)
     bool split_ok = false;
     int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged, 3 split tile (n=2048)
+    int nuss_variant = 0;  // 0 auto, 1 schoolbook row products, 2 recursive row products (Z_q)
     size_t smem_fused = 0, smem_one = 0, smem_tma = 0;
     std::atomic<uint64_t> launches{0};
     // host pipeline (qt_polymul_host): lazily created
@@ -466,6 +467,12 @@ int qt_set_fused_variant(qt_ctx* c, int variant) {
     return 0;
 }
 
+int qt_set_nussbaumer_variant(qt_ctx* c, int variant) {
+    if (!c || variant < NUSS_AUTO || variant > NUSS_RECURSIVE) return QT_ERR_BAD_ARG;
+    c->nuss_variant = variant;
+    return 0;
+}
+
 int qt_synchronize(qt_ctx* c) {
     if (!c) return QT_ERR_BAD_ARG;
     DeviceGuard g(c->device);
@@ -559,7 +566,7 @@ int qt_nussbaumer(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, 
     if (!c || ((!x || !y || !z) && B) || (ring != QT_RING_2P32M1 && ring != QT_RING_MODQ)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
     DeviceGuard g(c->device);
-    int rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, x, y, z, B, ring, c->stream);
+    int rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, x, y, z, B, ring, c->nuss_variant, c->stream);
     if (rc == 0) c->launches++;
     return rc;
 }
@@ -609,7 +616,7 @@ static int staged_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint
             if (!rc) rc = (int)cudaMemcpyAsync(dy, py ? hy : y + off, bytes, cudaMemcpyHostToDevice, s);
             if (!rc) {
                 if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
-                else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, s); if (!rc) c->launches++; }
+                else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, c->nuss_variant, s); if (!rc) c->launches++; }
             }
             if (!rc) rc = (int)cudaMemcpyAsync(pz ? hx : z + off, dx, bytes, cudaMemcpyDeviceToHost, s);
             const cudaError_t e = cudaStreamSynchronize(s);  // always: nothing of this chunk may stay in flight
@@ -652,7 +659,7 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
         if (!rc) rc = (int)cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s);
         if (!rc) {
             if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
-            else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, s); if (!rc) c->launches++; }
+            else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, c->nuss_variant, s); if (!rc) c->launches++; }
         }
         if (!rc) rc = (int)cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s);
         done += cnt;

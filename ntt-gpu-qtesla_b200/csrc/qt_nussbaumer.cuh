@@ -116,6 +116,146 @@ template <int SET> struct NussOpsLazy {
     static QT_HD uint32_t half(uint32_t a) { return a; }  // deferred: folded into the post-product constant
 };
 
+// ---- recursive row products -----------------------------------------------------------------------
+// "Nussbaumer recursive": the 2m products of length r are themselves negacyclic products mod (w^r + 1), so
+// the same split applies again instead of the schoolbook `naive` (NTT.cu:147-165; the reference does not
+// recurse).  r = MI*RI with MI | RI (32 = 4*8, 64 = 8*8): 2*MI schoolbook products of length 8 replace one of
+// length r — 512 instead of 1024 multiplications (r = 32), 1024 instead of 4096 (r = 64) — at the price of
+// log2(MI) forward and log2(MI)+1 inverse stages of additions.  Everything is thread-private: after
+// unrolling every index is a compile-time constant, so rows are registers, a rotation by w^sr is a renaming
+// and its sign turns an add into a subtract.  Z_q only (both arithmetic flavours); the ring 2^32-1 keeps the
+// reference's operation order and with it the reference's representation of zero.
+//   LAZYQ (q < 2^25): two's-complement residues, no reduction in the stages.  |x| <= BX, |y| <= BY on entry
+//     (static_assert'ed by the caller through fits()); a product accumulates in ONE signed 64-bit register,
+//     is Montgomery-reduced and multiplied (signed Shoup) by `fix` = 2^32 * 2^-(LOGMI+1) * (whatever the caller
+//     folds in), which pays for the halvings of the inner inverse in advance; the inner inverse and the
+//     recombination are additions (|v| < 24 q), one signed Shoup multiplication by 1 brings the output back
+//     to [-q/2, 3q/2).
+//   canonical (29/30-bit q): operands and result in [0, q); compare-subtract additions, accumulators of
+//     TERMS products, Montgomery reduction, the halvings and 2^32 in one final Shoup multiplication.
+template <int SET, uint32_t LEN, bool LAZYQ> struct NussInner {
+    using T = Tile<SET>;
+    static constexpr uint32_t Q = Cfg<SET>::Q;
+    static constexpr uint32_t MI = (LEN >= 64) ? 8 : 4, RI = LEN / MI, LOGMI = c_log2(MI), ROWS = 2 * MI;
+    static constexpr uint32_t UNIT = RI / MI;  // w^(RI/MI) is the 2*MI-th root of unity
+    static_assert(MI * RI == LEN && RI % MI == 0 && RI == 8, "inner split: MI | RI");
+    static constexpr uint32_t TERMS = LAZYQ ? RI : (T::QCAP >= 8 ? 8 : 4);  // products per 64-bit accumulator
+    static constexpr uint32_t INV_HALVES = c_powmod((Q + 1) / 2, LOGMI + 1, Q);  // 2^-(LOGMI+1)
+    // lazy ranges: inner forward values in an int32, RI products in an int64
+    static QT_CHD bool fits(uint64_t bx, uint64_t by) {
+        return by * MI < (1ull << 31) && bx * MI < (1ull << 31) && (bx * MI) * (by * MI) < ((1ull << 63) / RI);
+    }
+    // the constant a caller passes as `fix` when it wants the plain product (canonical) / the product times
+    // `extra` (LAZYQ, extra = whatever else it defers)
+    static QT_CHD uint32_t fix_value(uint32_t extra) { return c_mulmod(c_mulmod(T::C::R_MODQ, INV_HALVES, Q), extra, Q); }
+
+    static QT_HD uint32_t add(uint32_t a, uint32_t b) { return LAZYQ ? a + b : T::csub(a + b, Q); }
+    static QT_HD uint32_t sub(uint32_t a, uint32_t b) { return LAZYQ ? a - b : T::csub(a - b + Q, Q); }
+    static QT_HD uint32_t rot(uint32_t i, uint32_t j) { return (c_bitrev(i, LOGMI - j) << j) * UNIT; }
+
+    // rows V_i[a] = v[MI*a + i], rows MI..2MI-1 copies, then log2(MI) rotate-and-add stages
+    static QT_HD void forward(const uint32_t (&v)[LEN], uint32_t (&V)[ROWS][RI]) {
+#pragma unroll
+        for (uint32_t i = 0; i < MI; i++)
+#pragma unroll
+            for (uint32_t a = 0; a < RI; a++) V[i][a] = V[i + MI][a] = v[MI * a + i];
+#pragma unroll
+        for (int j = (int)LOGMI - 1; j >= 0; j--) {
+#pragma unroll
+            for (uint32_t bf = 0; bf < MI; bf++) {
+                const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+                const uint32_t I = (i << (j + 1)) + t, L = I + (1u << j), sr = rot(i, (uint32_t)j);
+                uint32_t lo[RI], hi[RI];
+#pragma unroll
+                for (uint32_t a = 0; a < RI; a++) {
+                    const uint32_t src = V[L][(a - sr) & (RI - 1)], vi = V[I][a];
+                    const bool wrap = a < sr;  // T[a] = -src on wrap-around
+                    lo[a] = wrap ? sub(vi, src) : add(vi, src);
+                    hi[a] = wrap ? add(vi, src) : sub(vi, src);
+                }
+#pragma unroll
+                for (uint32_t a = 0; a < RI; a++) { V[I][a] = lo[a]; V[L][a] = hi[a]; }
+            }
+        }
+    }
+
+    // one length-RI schoolbook product, output coefficient o
+    static QT_HD uint32_t dot(const uint32_t (&xr)[RI], const uint32_t (&yr)[RI], const uint32_t (&nyr)[RI], uint32_t o,
+                              TwPair fix) {
+        if (LAZYQ) {
+            int64_t acc = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < RI; j++) {
+                // wrapped terms enter negated (nyr = -yr)
+                acc += (int64_t)(int32_t)xr[j] * (int64_t)(int32_t)((j <= o) ? yr[(o - j) & (RI - 1)] : nyr[(o - j) & (RI - 1)]);
+            }
+            const uint32_t m = (uint32_t)acc * (0u - T::C::QINV_NEG);               // lo(acc) * q^-1
+            const uint32_t red = (uint32_t)(acc >> 32) - (uint32_t)mulhi32s(m, Q);  // acc * 2^-32, |red| < 2^31
+            return T::smul_shoup(red, fix);                                         // [-q/2, 3q/2)
+        }
+        uint32_t r = 0;
+#pragma unroll
+        for (uint32_t g = 0; g < RI / TERMS; g++) {
+            uint64_t acc = 0;
+#pragma unroll
+            for (uint32_t jj = 0; jj < TERMS; jj++) {
+                const uint32_t j = g * TERMS + jj;
+                acc += (uint64_t)xr[j] * ((j <= o) ? yr[(o - j) & (RI - 1)] : nyr[(o - j) & (RI - 1)]);
+            }
+            const uint32_t m = (uint32_t)acc * T::C::QINV_NEG;                // Montgomery: acc * 2^-32
+            const uint32_t red = (uint32_t)((acc + (uint64_t)m * Q) >> 32);  // [0, 2q)
+            r = (g == 0) ? red : r + red;
+        }
+        return (RI / TERMS == 1) ? T::csub(r, Q) : T::csub(T::fold2q(r), Q);
+    }
+
+    // z = x (*) y * fix * 2^-32 * 2^(LOGMI+1) mod (w^LEN + 1, q); LAZYQ: fix is a signed Shoup pair and z lies in
+    // [-q/2, 3q/2); canonical: fix is an unsigned Shoup pair and z in [0, q).
+    static QT_HD void product(const uint32_t (&x)[LEN], const uint32_t (&y)[LEN], uint32_t (&z)[LEN], TwPair fix) {
+        uint32_t X[ROWS][RI], Y[ROWS][RI];
+        forward(x, X);
+        forward(y, Y);
+#pragma unroll
+        for (uint32_t k = 0; k < ROWS; k++) {
+            uint32_t ny[RI], out[RI];
+#pragma unroll
+            for (uint32_t a = 0; a < RI; a++) ny[a] = LAZYQ ? 0u - Y[k][a] : Q - Y[k][a];
+#pragma unroll
+            for (uint32_t o = 0; o < RI; o++) out[o] = dot(X[k], Y[k], ny, o, fix);
+#pragma unroll
+            for (uint32_t o = 0; o < RI; o++) X[k][o] = out[o];  // Z_k over X_k
+        }
+        // inverse stages, halvings deferred (NTT.cu:241-269 applied to the inner split)
+#pragma unroll
+        for (uint32_t j = 0; j <= LOGMI; j++) {
+#pragma unroll
+            for (uint32_t bf = 0; bf < MI; bf++) {
+                const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+                const uint32_t A = (i << (j + 1)) + t, B = A + (1u << j), sr = (j == LOGMI) ? 0u : rot(i, j);
+                uint32_t d[RI];
+#pragma unroll
+                for (uint32_t a = 0; a < RI; a++) {
+                    const uint32_t za = X[A][a], zb = X[B][a];
+                    X[A][a] = add(za, zb);
+                    // Z_B = (Z_A - Z_B) * w^-sr: position a - sr takes the difference at a, negated on wrap-around
+                    d[a] = (a >= sr) ? sub(za, zb) : sub(zb, za);
+                }
+#pragma unroll
+                for (uint32_t a = 0; a < RI; a++) X[B][(a - sr) & (RI - 1)] = d[a];
+            }
+        }
+        // recombination with u^MI = w (NTT.cu:271-276)
+        const TwPair one{1u, T::C::MU32};
+#pragma unroll
+        for (uint32_t i = 0; i < MI; i++)
+#pragma unroll
+            for (uint32_t a = 0; a < RI; a++) {
+                const uint32_t v = (a == 0) ? sub(X[i][0], X[MI + i][RI - 1]) : add(X[i][a], X[MI + i][a - 1]);
+                z[MI * a + i] = LAZYQ ? T::smul_shoup(v, one) : T::csub(T::mul_shoup(v, fix), Q);
+            }
+    }
+};
+
 template <int SET, int RING> struct Nuss {
     using K = NussCfg<SET>;
     using O = NussOps<SET, RING>;
@@ -253,6 +393,17 @@ template <int SET, int RING> struct Nuss {
         }
     }
 
+    // product phase, recursive form (Z_q): the row product is split once more (NussInner)
+    static QT_HD void product_recursive(uint32_t* xr, const uint32_t* yr) {
+        using IN = NussInner<SET, R, false>;
+        uint32_t x[R], y[R], zz[R];
+#pragma unroll
+        for (uint32_t j = 0; j < R; j++) { x[j] = xr[j]; y[j] = yr[j]; }
+        IN::product(x, y, zz, tw_unsigned_c(IN::fix_value(1u), Q));
+#pragma unroll
+        for (uint32_t j = 0; j < R; j++) xr[j] = zz[j];
+    }
+
     // final phase: recombination and coalesced store (NTT.cu:271-276)
     static QT_HD void store(uint32_t tid, uint32_t nthreads, const uint32_t* z, uint32_t* gz) {
         for (uint32_t g = tid; g < K::N; g += nthreads) {
@@ -267,9 +418,10 @@ template <int SET, int RING> struct Nuss {
 
 #if defined(__CUDACC__)
 
-template <int SET, int RING>
+template <int SET, int RING, bool REC = false>
 __global__ void __launch_bounds__(NussCfg<SET>::THREADS)
 k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    static_assert(!REC || RING == 1, "recursive row products exist for Z_q only");
     using K = NussCfg<SET>;
     using NU = Nuss<SET, RING>;
     extern __shared__ uint4 nuss_smem_raw[];
@@ -305,8 +457,12 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
         // products: one thread per row
         {
             const uint32_t p = tid / K::ROWS, row = tid % K::ROWS;
-            if (p < np)
-                NU::product(smem + p * K::POLY_WORDS + row * K::XS, smem + p * K::POLY_WORDS + K::X_WORDS + row * K::YS);
+            if (p < np) {
+                uint32_t* xr = smem + p * K::POLY_WORDS + row * K::XS;
+                uint32_t* yr = smem + p * K::POLY_WORDS + K::X_WORDS + row * K::YS;
+                if constexpr (REC) NU::product_recursive(xr, yr);
+                else NU::product(xr, yr);
+            }
         }
         __syncthreads();
         // inverse stages on Z (in the X rows)
@@ -338,9 +494,10 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
 // lane = row; each lane multiplies its row(s) privately: 32x32 multiply-accumulates from registers.
 // Z_q mode accumulates 64-bit products lazily and Montgomery-reduces once per accumulator; the common
 // factor 2^-32 is removed by one Shoup multiplication per output coefficient at the very end.
-template <int SET, int RING> struct NussWarp {
+template <int SET, int RING, bool REC = false> struct NussWarp {
     using K = NussCfg<SET>;
     using T = Tile<SET>;
+    static_assert(!REC || RING == 1, "recursive row products exist for Z_q only");
     static constexpr bool LAZYQ = (RING == 1) && T::LAZY;  // signed-lazy Z_q (see NussOpsLazy)
     using O = typename std::conditional<LAZYQ, NussOpsLazy<SET>, NussOps<SET, RING>>::type;
     static constexpr uint32_t M = K::M, LOGM = K::LOGM, ROWS = K::ROWS, Q = K::Q;
@@ -349,7 +506,10 @@ template <int SET, int RING> struct NussWarp {
     static_assert(!LAZYQ || ((uint64_t)(3u << (LOGM + 1)) * Q < (1ull << 31)), "lazy inverse range");
     static constexpr uint32_t RS = 33;                                   // row stride in shared memory
     static constexpr uint32_t WARP_WORDS = 2 * ROWS * RS;                // X rows then Y rows
-    static constexpr uint32_t WARPS = 12;  // 12 x 16.9 KiB of rows, <= 170 registers: one CTA per SM
+#ifndef QT_NUSS_WARPS
+#define QT_NUSS_WARPS 12
+#endif
+    static constexpr uint32_t WARPS = QT_NUSS_WARPS;  // 12 x 16.9 KiB of rows, <= 170 registers: one CTA per SM
     static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_WORDS * sizeof(uint32_t);
     static constexpr uint32_t RPL = ROWS / 32;                           // rows per lane in the product phase
     // terms a 64-bit accumulator may take before a Montgomery reduction: sum < q * 2^32
@@ -398,12 +558,30 @@ template <int SET, int RING> struct NussWarp {
         }
     }
 
+    // recursive row products (REC): ranges of the signed-lazy flavour.  The forward stages leave |v| <= 2^LOGM * |input|;
+    // where two uncentred operands would overflow the 64-bit accumulator of the inner products, x is centred to
+    // (-q/2, q/2] when it is loaded (CENTRE_X; two instructions per coefficient).
+    using Inner = NussInner<SET, 32, LAZYQ>;
+    static constexpr bool CENTRE_X = REC && LAZYQ && !Inner::fits((uint64_t)Q << LOGM, (uint64_t)Q << LOGM);
+    static_assert(!(REC && LAZYQ) || Inner::fits((uint64_t)(CENTRE_X ? Q / 2 + 1 : Q) << LOGM, (uint64_t)Q << LOGM),
+                  "inner product accumulator");
+
     // one row: z = x (*) y negacyclic, length 32; x, y, z are shared-memory rows (z overwrites x)
     static __device__ __forceinline__ void product_row(uint32_t* xr, const uint32_t* yr) {
         uint32_t x[32], y[32];
 #pragma unroll
         for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
-        if (RING == 0) {
+        if (REC) {
+            // same output convention as the schoolbook branches below: LAZYQ — product * 2^-(LOGM+1) in
+            // [-q/2, 3q/2); canonical — product * 2^-32 in [0, q)
+            constexpr uint32_t EXTRA = LAZYQ ? c_powmod((Q + 1) / 2, LOGM + 1, Q) : c_powmod(T::C::R_MODQ, Q - 2, Q);
+            constexpr uint32_t FIX = Inner::fix_value(EXTRA);
+            const TwPair fix = LAZYQ ? tw_signed_c(FIX, Q) : tw_unsigned_c(FIX, Q);
+            uint32_t zz[32];
+            Inner::product(x, y, zz, fix);
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) xr[j] = zz[j];
+        } else if (RING == 0) {
             // naive (NTT.cu:147-165) keeps two chains per output, A over j <= k and B over j > k, folding
             // after every term.  A chain's final value is a function of the INTEGER sum T of its products
             // only: it is congruent to T, lies in [0, 2^32-1], and is 0 exactly when T = 0 (a fold of a
@@ -469,10 +647,10 @@ template <int SET, int RING> struct NussWarp {
     }
 };
 
-template <int SET, int RING>
-__global__ void __launch_bounds__(NussWarp<SET, RING>::WARPS * 32)
+template <int SET, int RING, bool REC = false>
+__global__ void __launch_bounds__(NussWarp<SET, RING, REC>::WARPS * 32)
 k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
-    using W = NussWarp<SET, RING>;
+    using W = NussWarp<SET, RING, REC>;
     using K = NussCfg<SET>;
     using O = typename W::O;
     using T = Tile<SET>;
@@ -494,6 +672,11 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
             for (uint32_t c = 0; c < K::M / 4; c++) {
                 const uint4 u = g[c];
                 v[4 * c] = u.x; v[4 * c + 1] = u.y; v[4 * c + 2] = u.z; v[4 * c + 3] = u.w;
+            }
+            if (W::CENTRE_X) {
+                const uint32_t thr = op ? 0xFFFFFFFFu : T::Q / 2;  // x only
+#pragma unroll
+                for (uint32_t i = 0; i < K::M; i++) v[i] -= (v[i] > thr) ? T::Q : 0u;
             }
 #pragma unroll
             for (uint32_t i = 0; i < K::M; i++) v[i + K::M] = v[i];  // rows m..2m-1 are copies (NTT.cu:187-191)
@@ -529,68 +712,61 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
     }
 }
 
+// Row products of the Z_q kernels: schoolbook (the reference's structure) or split once more (NussInner).
+// QT_NUSS_AUTO_RECURSIVE is what "automatic" picks.
+#ifndef QT_NUSS_AUTO_RECURSIVE
+#define QT_NUSS_AUTO_RECURSIVE 1
+#endif
+enum : int { NUSS_AUTO = 0, NUSS_SCHOOLBOOK = 1, NUSS_RECURSIVE = 2 };
+
+template <class Kern> int nuss_prepare(Kern k, int threads, size_t smem, int* occ_min) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int o = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, threads, smem);
+    if (e != cudaSuccess) return (int)e;
+    *occ_min = o < *occ_min ? o : *occ_min;
+    return 0;
+}
+
 template <int SET> int nuss_setup(int num_sms, int* grid) {
     using K = NussCfg<SET>;
-    cudaError_t e;
+    int occ = 64, rc = 0;
     if constexpr (K::R == 32) {  // warp-resident kernels
-        int occ = 64;
-        {
-            using W = NussWarp<SET, 0>;
-            e = cudaFuncSetAttribute(k_nussbaumer_warp<SET, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM_BYTES);
-            if (e != cudaSuccess) return (int)e;
-            int o = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_nussbaumer_warp<SET, 0>, W::WARPS * 32, W::SMEM_BYTES);
-            if (e != cudaSuccess) return (int)e;
-            occ = o < occ ? o : occ;
-        }
-        {
-            using W = NussWarp<SET, 1>;
-            e = cudaFuncSetAttribute(k_nussbaumer_warp<SET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM_BYTES);
-            if (e != cudaSuccess) return (int)e;
-            int o = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_nussbaumer_warp<SET, 1>, W::WARPS * 32, W::SMEM_BYTES);
-            if (e != cudaSuccess) return (int)e;
-            occ = o < occ ? o : occ;
-        }
-        *grid = (occ < 1 ? 1 : occ) * num_sms;
-        return 0;
-    }
-    e = cudaFuncSetAttribute(k_nussbaumer<SET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nussbaumer<SET, 1>, K::THREADS, K::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    {
-        int occ0 = 0;
-        e = cudaFuncSetAttribute(k_nussbaumer<SET, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k_nussbaumer<SET, 0>, K::THREADS, K::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        occ = occ0 < occ ? occ0 : occ;
+        using W = NussWarp<SET, 0>;  // every variant has the same CTA shape
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 0, false>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, false>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, true>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+    } else {
+        if ((rc = nuss_prepare(k_nussbaumer<SET, 0, false>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer<SET, 1, false>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer<SET, 1, true>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
     }
     *grid = (occ < 1 ? 1 : occ) * num_sms;
     return 0;
 }
 
 template <int SET>
-int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring, cudaStream_t s) {
+int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring, int variant,
+                cudaStream_t s) {
     using K = NussCfg<SET>;
+    const bool rec = ring == 1 && (variant == NUSS_RECURSIVE || (variant == NUSS_AUTO && QT_NUSS_AUTO_RECURSIVE));
     if constexpr (K::R == 32) {
         if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15) != 0) return -2;  // 128-bit accesses
-        using W0 = NussWarp<SET, 0>;
+        using W = NussWarp<SET, 0>;
         const int g = (int)(batch < (size_t)max_grid ? batch : (size_t)max_grid);  // small batches spread over all SMs
-        if (ring == 0) k_nussbaumer_warp<SET, 0><<<g, W0::WARPS * 32, W0::SMEM_BYTES, s>>>(x, y, z, batch);
-        else k_nussbaumer_warp<SET, 1><<<g, NussWarp<SET, 1>::WARPS * 32, NussWarp<SET, 1>::SMEM_BYTES, s>>>(x, y, z, batch);
+        if (ring == 0) k_nussbaumer_warp<SET, 0, false><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        else if (rec) k_nussbaumer_warp<SET, 1, true><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        else k_nussbaumer_warp<SET, 1, false><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        return (int)cudaGetLastError();
+    } else {
+        const size_t groups = (batch + K::P - 1) / K::P;
+        const int grid = (int)(groups < (size_t)max_grid ? groups : (size_t)max_grid);
+        if (ring == 0) k_nussbaumer<SET, 0, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+        else if (rec) k_nussbaumer<SET, 1, true><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+        else k_nussbaumer<SET, 1, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
         return (int)cudaGetLastError();
     }
-    const size_t groups = (batch + K::P - 1) / K::P;
-    const int grid = (int)(groups < (size_t)max_grid ? groups : (size_t)max_grid);
-    if (ring == 0) {
-        k_nussbaumer<SET, 0><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
-    } else {
-        k_nussbaumer<SET, 1><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
-    }
-    return (int)cudaGetLastError();
 }
 
 #endif  // __CUDACC__

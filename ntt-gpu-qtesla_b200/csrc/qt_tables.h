@@ -54,6 +54,8 @@ QT_CHD TwPair tw_signed_c(uint32_t w, uint32_t q) {
     return TwPair{(uint32_t)(int32_t)wc, (uint32_t)(int32_t)fl};
 }
 
+QT_CHD TwPair tw_unsigned_c(uint32_t w, uint32_t q) { return TwPair{w, (uint32_t)(((uint64_t)w << 32) / q)}; }
+
 inline void put_slot(std::vector<TwQuad>& v, size_t base, uint32_t slot, uint32_t stride, uint32_t lane, TwPair t) {
     TwQuad& qd = v[base + (size_t)(slot / 2) * stride + lane];
     if (slot & 1) { qd.w1 = t.w; qd.ws1 = t.ws; }

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "qt_set_stream": (C.c_int, [_vp, _vp]),
     "qt_synchronize": (C.c_int, [_vp]),
     "qt_set_fused_variant": (C.c_int, [_vp, C.c_int]),
+    "qt_set_nussbaumer_variant": (C.c_int, [_vp, C.c_int]),
     "qt_device_malloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "qt_device_free": (C.c_int, [_vp, _vp]),
     "qt_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
@@ -167,6 +168,10 @@ class Engine:
     def set_fused_variant(self, variant):
         """0 automatic, 1 direct coalesced loads, 2 TMA bulk copies staged through shared memory"""
         _check(lib().qt_set_fused_variant(self._h, variant))
+
+    def set_nussbaumer_variant(self, variant):
+        """row products of the Z_q Nussbaumer kernels: 0 automatic, 1 schoolbook, 2 recursive (split once more)"""
+        _check(lib().qt_set_nussbaumer_variant(self._h, variant))
 
     def synchronize(self):
         _check(lib().qt_synchronize(self._h))

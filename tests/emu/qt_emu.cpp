@@ -266,7 +266,7 @@ template <int SET> Emu<SET>& emu() {
 
 // Nussbaumer: same phase sequence as k_nussbaumer; warps run read-all-lanes then write-all-lanes,
 // threads of a phase run one after another between the kernel's __syncthreads points.
-template <int SET, int RING> int emu_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+template <int SET, int RING, bool REC = false> int emu_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
     using K = NussCfg<SET>;
     using NU = Nuss<SET, RING>;
     std::vector<uint32_t> smem(K::P * K::POLY_WORDS);
@@ -295,9 +295,12 @@ template <int SET, int RING> int emu_nussbaumer(const uint32_t* x, const uint32_
                 }
         for (uint32_t tid = 0; tid < K::THREADS; tid++) {
             const uint32_t p = tid / K::ROWS, row = tid % K::ROWS;
-            if (p < np)
-                NU::product(smem.data() + p * K::POLY_WORDS + row * K::XS,
-                            smem.data() + p * K::POLY_WORDS + K::X_WORDS + row * K::YS);
+            if (p < np) {
+                uint32_t* xr = smem.data() + p * K::POLY_WORDS + row * K::XS;
+                uint32_t* yr = smem.data() + p * K::POLY_WORDS + K::X_WORDS + row * K::YS;
+                if (REC) NU::product_recursive(xr, yr);
+                else NU::product(xr, yr);
+            }
         }
         for (uint32_t j = 0; j <= K::LOGM; j++)
             for (uint32_t warp = 0; warp < WARPS; warp++)
@@ -313,6 +316,21 @@ template <int SET, int RING> int emu_nussbaumer(const uint32_t* x, const uint32_
             const uint32_t p = tid / per;
             if (p < np) NU::store(tid % per, per, smem.data() + p * K::POLY_WORDS, z + (p0 + p) * K::N);
         }
+    }
+    return 0;
+}
+
+// The signed-lazy flavour of NussInner as the warp-resident kernel calls it (length 32, q < 2^25): x, y are
+// two's-complement words with |x| <= bx, |y| <= by; returns z * 1 (fix = the plain-product constant) in
+// [-q/2, 3q/2).  rows products at once.
+template <int SET> int emu_inner_lazy(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t rows) {
+    using IN = NussInner<SET, 32, true>;
+    const TwPair fix = tw_signed_c(IN::fix_value(1u), Cfg<SET>::Q);
+    for (size_t r = 0; r < rows; r++) {
+        uint32_t xa[32], ya[32], za[32];
+        for (int j = 0; j < 32; j++) { xa[j] = x[32 * r + j]; ya[j] = y[32 * r + j]; }
+        IN::product(xa, ya, za, fix);
+        for (int j = 0; j < 32; j++) z[32 * r + j] = za[j];
     }
     return 0;
 }
@@ -362,6 +380,23 @@ int qtemu_nussbaumer(int set, const uint32_t* x, const uint32_t* y, uint32_t* z,
     case 5: return emu_nussbaumer<SET_P_I, 1>(x, y, z, batch);
     case 6: return emu_nussbaumer<SET_P_III, 0>(x, y, z, batch);
     case 7: return emu_nussbaumer<SET_P_III, 1>(x, y, z, batch);
+    default: return -1;
+    }
+}
+// recursive row products (k_nussbaumer<SET, 1, true>): same phases, NussInner instead of the schoolbook
+int qtemu_nussbaumer_recursive(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    switch (set) {
+    case SET_I: return emu_nussbaumer<SET_I, 1, true>(x, y, z, batch);
+    case SET_III: return emu_nussbaumer<SET_III, 1, true>(x, y, z, batch);
+    case SET_P_I: return emu_nussbaumer<SET_P_I, 1, true>(x, y, z, batch);
+    case SET_P_III: return emu_nussbaumer<SET_P_III, 1, true>(x, y, z, batch);
+    default: return -1;
+    }
+}
+int qtemu_inner_lazy(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t rows) {
+    switch (set) {
+    case SET_I: return emu_inner_lazy<SET_I>(x, y, z, rows);
+    case SET_III: return emu_inner_lazy<SET_III>(x, y, z, rows);
     default: return -1;
     }
 }

@@ -27,6 +27,8 @@ def emu():
     L.qtemu_polymul_split.argtypes = [u, u, u, C.c_size_t]
     L.qtemu_inverse_natural.argtypes = [C.c_int, u, C.c_size_t]
     L.qtemu_nussbaumer.argtypes = [C.c_int, u, u, u, C.c_size_t, C.c_int]
+    L.qtemu_nussbaumer_recursive.argtypes = [C.c_int, u, u, u, C.c_size_t]
+    L.qtemu_inner_lazy.argtypes = [C.c_int, u, u, u, C.c_size_t]
     return L
 
 
@@ -108,3 +110,62 @@ def test_emulated_nussbaumer_equals_oracle(emu, oracle, s):
     yr[2 * p.n + rng.choice(p.n, 40, replace=False)] = 0xFFFFFFFE
     rc = emu.qtemu_nussbaumer(s, _p(xr), _p(yr), _p(z), B, 0)               # ring 2^32-1, bit-exact incl. zeros
     assert rc == 0 and np.array_equal(z, oracle.nussbaumer(p.n, xr, yr))
+
+
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_emulated_recursive_nussbaumer_equals_oracle(emu, oracle, s):
+    """k_nussbaumer<SET, Z_q, recursive>: the 2m row products split once more (NussInner, canonical flavour)."""
+    p = oracle.params(s)
+    B = 6
+    rng = np.random.default_rng(20 + s)
+    x = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    y = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    x[: p.n] = p.q - 1; y[: p.n] = p.q - 1
+    x[p.n: 2 * p.n] = p.q - 1; y[p.n: 2 * p.n] = np.where(np.arange(p.n) % 2 == 0, p.q - 1, 0)
+    x[2 * p.n: 3 * p.n] = 0
+    z = np.zeros_like(x)
+    assert emu.qtemu_nussbaumer_recursive(s, _p(x), _p(y), _p(z), B) == 0
+    assert np.array_equal(z, oracle.polymul(s, x, y))
+
+
+def _negacyclic_rows(x, y, q):
+    """exact negacyclic products of length-32 rows of Python integers, mod q"""
+    out = np.zeros_like(x)
+    for r in range(x.shape[0]):
+        for k in range(32):
+            acc = 0
+            for j in range(32):
+                t = int(x[r, j]) * int(y[r, (k - j) % 32])
+                acc += t if j <= k else -t
+            out[r, k] = acc % q
+    return out
+
+
+@pytest.mark.parametrize("s", [SET_I, SET_III])
+def test_inner_lazy_product_ranges(emu, oracle, s):
+    """Signed-lazy NussInner as the warp-resident kernel feeds it: operands at the bounds the kernel
+    static_asserts (|x| <= 2^LOGM * q/2 centred for qTESLA-III, 2^LOGM * q otherwise; |y| <= 2^LOGM * q), all
+    sign patterns; the result must be the exact product mod q and lie in [-q/2, 3q/2)."""
+    p = oracle.params(s)
+    q = p.q
+    logm = 4 if p.n == 512 else 5
+    bx = ((q // 2 + 1) if s == SET_III else q) << logm
+    by = q << logm
+    rng = np.random.default_rng(30 + s)
+    rows = 24
+    x = rng.integers(-bx, bx + 1, (rows, 32), dtype=np.int64)
+    y = rng.integers(-by, by + 1, (rows, 32), dtype=np.int64)
+    x[0, :] = bx; y[0, :] = by                       # all terms of one sign at maximum magnitude
+    x[1, :] = -bx; y[1, :] = by
+    x[2, :] = bx; y[2, :] = np.where(np.arange(32) % 2 == 0, by, -by)
+    x[3, :] = np.where(np.arange(32) % 8 < 4, bx, -bx); y[3, :] = -by
+    x[4, :] = 0
+    x[5, :] = 0; x[5, 31] = 1; y[5, :] = 0; y[5, 1] = 1   # X^31 * X = -1
+    xu = x.astype(np.int32).view(np.uint32).ravel().copy()
+    yu = y.astype(np.int32).view(np.uint32).ravel().copy()
+    z = np.zeros_like(xu)
+    assert emu.qtemu_inner_lazy(s, _p(xu), _p(yu), _p(z), rows) == 0
+    zs = z.view(np.int32).astype(np.int64).reshape(rows, 32)
+    assert zs.min() >= -(q // 2) - 1 and zs.max() < 3 * q // 2 + 1
+    assert np.array_equal(zs % q, _negacyclic_rows(x, y, q))
+    assert zs[5, 0] % q == q - 1

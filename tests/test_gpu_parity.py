@@ -361,8 +361,9 @@ def test_nussbaumer_ring_other_sizes(engines, oracle, golden, qt, s):
     assert sha(z0) == golden[name + "_ring_schoolbook_b1_sha256"]
 
 
+@pytest.mark.parametrize("nv", [0, 1, 2])  # row products: automatic, schoolbook, recursive
 @pytest.mark.parametrize("s", ALL_SETS)
-def test_nussbaumer_modq_equals_ntt(engines, oracle, qt, s):
+def test_nussbaumer_modq_equals_ntt(engines, oracle, qt, s, nv):
     import torch
     eng = engines[s]
     B = 9
@@ -373,15 +374,49 @@ def test_nussbaumer_modq_equals_ntt(engines, oracle, qt, s):
     x[n:2 * n] = q - 1; y[n:2 * n] = np.where(np.arange(n) % 2 == 0, q - 1, 0)
     x[2 * n:3 * n] = np.where(np.arange(n) % 64 < 32, q - 1, 0); y[2 * n:3 * n] = q - 1
     x[3 * n:4 * n] = 0
+    x[4 * n:5 * n] = q // 2 + 1; y[4 * n:5 * n] = q - 1          # just above the centring threshold of the recursive rows
+    x[5 * n:6 * n] = q // 2; y[5 * n:6 * n] = np.where(np.arange(n) % 8 < 4, q - 1, 1)
     tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda(); tz = torch.empty_like(tx)
+    eng.set_nussbaumer_variant(nv)
     try:
         eng.nussbaumer(tx, ty, tz, qt.RING_MODQ)
-    except qt.QtError as e:
-        if "unsupported" in str(e):
-            pytest.skip("Nussbaumer kernel not built yet")
-        raise
-    eng.synchronize()
+        eng.synchronize()
+    finally:
+        eng.set_nussbaumer_variant(0)
     assert np.array_equal(tz.cpu().numpy().view(np.uint32), oracle.polymul(s, x, y))
+
+
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_nussbaumer_row_variants_agree_at_size(engines, oracle, qt, s):
+    """schoolbook and recursive row products: identical results on a batch that fills every SM several times, a
+    sample of it checked against the oracle; the ring 2^32-1 ignores the variant."""
+    import torch
+    eng = engines[s]
+    n, q = eng.n, eng.q
+    B = 4099 if n < 2048 else 1031
+    x, y = rand_pair(q, B * n, 777 + s)
+    tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda()
+    outs = {}
+    for nv in (1, 2):
+        tz = torch.empty_like(tx)
+        eng.set_nussbaumer_variant(nv)
+        try:
+            eng.nussbaumer(tx, ty, tz, qt.RING_MODQ)
+            eng.synchronize()
+            outs[nv] = tz.cpu().numpy().view(np.uint32)
+            tr = torch.empty_like(tx)
+            eng.nussbaumer(tx, ty, tr, qt.RING_2P32M1)
+            eng.synchronize()
+            outs[("ring", nv)] = tr.cpu().numpy().view(np.uint32)
+        finally:
+            eng.set_nussbaumer_variant(0)
+    assert np.array_equal(outs[1], outs[2])
+    assert np.array_equal(outs[("ring", 1)], outs[("ring", 2)])
+    k = 40 * n
+    assert np.array_equal(outs[2][:k], oracle.polymul(s, x[:k], y[:k]))
+    assert np.array_equal(outs[2][-k:], oracle.polymul(s, x[-k:], y[-k:]))
+    with pytest.raises(qt.QtError):
+        eng.set_nussbaumer_variant(3)
 
 
 def test_cxx_harness_reference_command_line():
