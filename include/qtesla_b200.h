@@ -90,8 +90,9 @@ int qt_synchronize(qt_ctx* ctx);
  * with the polynomial processed as two 1024-point halves (what "automatic" picks for qTESLA-p-III) */
 int qt_set_fused_variant(qt_ctx* ctx, int variant);
 /* row products of the Z_q Nussbaumer kernels: 0 = automatic, 1 = schoolbook (the structure of the reference's
- * `naive`, NTT.cu:147-165), 2 = recursive (the 2m length-r products are split once more, 32 = 4*8 / 64 = 8*8).
- * Results are identical; the ring 2^32-1 always uses the reference's schoolbook order. */
+ * `naive`, NTT.cu:147-165), 2 = recursive (the 2m length-r products are split once more, 32 = 4*8 / 64 = 8*8),
+ * 3 = schoolbook on the FP64 pipe with exact double-precision accumulation (q < 2^25 only, else
+ * QT_ERR_UNSUPPORTED).  Results are identical; the ring 2^32-1 always uses the reference's schoolbook order. */
 int qt_set_nussbaumer_variant(qt_ctx* ctx, int variant);
 int qt_device_malloc(qt_ctx* ctx, size_t bytes, void** out_dev);
 int qt_device_free(qt_ctx* ctx, void* dev);

@@ -468,7 +468,8 @@ int qt_set_fused_variant(qt_ctx* c, int variant) {
 }
 
 int qt_set_nussbaumer_variant(qt_ctx* c, int variant) {
-    if (!c || variant < NUSS_AUTO || variant > NUSS_RECURSIVE) return QT_ERR_BAD_ARG;
+    if (!c || variant < NUSS_AUTO || variant > NUSS_FP64) return QT_ERR_BAD_ARG;
+    if (variant == NUSS_FP64 && !QT_DISPATCH(c, nuss_has_f64)) return QT_ERR_UNSUPPORTED;
     c->nuss_variant = variant;
     return 0;
 }

@@ -20,6 +20,7 @@
 //   * __syncthreads only between phases.
 // The phase functions are __host__ __device__ so tests/emu can run them thread by thread.
 #pragma once
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <type_traits>
@@ -253,6 +254,36 @@ template <int SET, uint32_t LEN, bool LAZYQ> struct NussInner {
                 const uint32_t v = (a == 0) ? sub(X[i][0], X[MI + i][RI - 1]) : add(X[i][a], X[MI + i][a - 1]);
                 z[MI * a + i] = LAZYQ ? T::smul_shoup(v, one) : T::csub(T::mul_shoup(v, fix), Q);
             }
+    }
+};
+
+// ---- row products on the FP64 pipe ------------------------------------------------------------------
+// B200 issues DFMA at 64 lanes/clk/SM: twice the rate of the 32x32->64 integer multiply-add (IMAD.WIDE, 32
+// lanes/clk/SM, profiles/ubench_*.json) and on a pipe of its own, so the row products stop competing with the
+// stage arithmetic for the integer multiply pipe.  Exactness: both operands are first brought to [-q/2, 3q/2)
+// (one signed Shoup multiplication each, which also carries the deferred halvings); a product is then below
+// 2.25 q^2 and ANY partial sum of the 32 terms of an output below 72 q^2 < 2^53 — every DFMA is exact, in any
+// order.  The sum is reduced with the rounded quotient t = rint(acc / q) (magic-number rounding) and
+// r = acc - t q, again exact, |r| <= q/2 + 1.  q < 2^25 only (the signed-lazy sets).
+template <int SET> struct NussRowF64 {
+    using T = Tile<SET>;
+    static constexpr uint32_t Q = Cfg<SET>::Q;
+    static constexpr bool OK = T::LAZY && 72.0 * (double)Q * (double)Q < 9007199254740992.0;
+    // z = x (*) y mod (w^32 + 1, q) for two's-complement x, y in [-q/2, 3q/2); z in [-q/2 - 1, q/2 + 1]
+    static QT_HD void product(const uint32_t (&x)[32], const uint32_t (&y)[32], uint32_t (&z)[32]) {
+        double xd[32], yd[32];
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j++) { xd[j] = (double)(int32_t)x[j]; yd[j] = (double)(int32_t)y[j]; }
+        const double INVQ = 1.0 / (double)Q, QD = (double)Q, MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+#pragma unroll
+        for (uint32_t k = 0; k < 32; k++) {
+            double acc = 0.0;
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++)  // wrapped terms enter negated
+                acc = (j <= k) ? fma(xd[j], yd[(k - j) & 31], acc) : fma(-xd[j], yd[(32 + k - j) & 31], acc);
+            const double t = fma(acc, INVQ, MAGIC) - MAGIC;  // rint(acc / q)
+            z[k] = (uint32_t)(int32_t)fma(-t, QD, acc);
+        }
     }
 };
 
@@ -494,11 +525,15 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
 // lane = row; each lane multiplies its row(s) privately: 32x32 multiply-accumulates from registers.
 // Z_q mode accumulates 64-bit products lazily and Montgomery-reduces once per accumulator; the common
 // factor 2^-32 is removed by one Shoup multiplication per output coefficient at the very end.
-template <int SET, int RING, bool REC = false> struct NussWarp {
+// MODE: row products — 0 schoolbook on the integer pipe (the reference's structure), 1 recursive (NussInner),
+// 2 schoolbook on the FP64 pipe (NussRowF64)
+template <int SET, int RING, int MODE = 0> struct NussWarp {
+    static constexpr bool REC = MODE == 1, F64 = MODE == 2;
     using K = NussCfg<SET>;
     using T = Tile<SET>;
-    static_assert(!REC || RING == 1, "recursive row products exist for Z_q only");
+    static_assert(MODE == 0 || RING == 1, "recursive / FP64 row products exist for Z_q only");
     static constexpr bool LAZYQ = (RING == 1) && T::LAZY;  // signed-lazy Z_q (see NussOpsLazy)
+    static_assert(!F64 || (LAZYQ && NussRowF64<SET>::OK), "FP64 row products need q < 2^25");
     using O = typename std::conditional<LAZYQ, NussOpsLazy<SET>, NussOps<SET, RING>>::type;
     static constexpr uint32_t M = K::M, LOGM = K::LOGM, ROWS = K::ROWS, Q = K::Q;
     // ranges of the lazy variant: 32 products of two forward outputs in an int64; 3 * 2^(LOGM+1) q in an int32
@@ -509,7 +544,13 @@ template <int SET, int RING, bool REC = false> struct NussWarp {
 #ifndef QT_NUSS_WARPS
 #define QT_NUSS_WARPS 12
 #endif
-    static constexpr uint32_t WARPS = QT_NUSS_WARPS;  // 12 x 16.9 KiB of rows, <= 170 registers: one CTA per SM
+    // 12 x 16.9 KiB of rows, <= 170 registers: one CTA per SM.  The recursive row products want more registers
+    // (two 8x8 row blocks live at once): 8 warps with up to 255 registers measured faster for the 64-row sets
+    // (qTESLA-III 78.5 vs 74.6 M polymul/s, p-I 57.7 vs 53.1; qTESLA-I, 32 rows: 182.8 vs 189.7).
+#ifndef QT_NUSS_F64_WARPS
+#define QT_NUSS_F64_WARPS 8  // 183 / 221 registers without spills; 12 warps (168 registers, 240 B spilled): 75.7 vs 81.6 M polymul/s
+#endif
+    static constexpr uint32_t WARPS = F64 ? QT_NUSS_F64_WARPS : (REC && ROWS == 64) ? 8 : QT_NUSS_WARPS;
     static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_WORDS * sizeof(uint32_t);
     static constexpr uint32_t RPL = ROWS / 32;                           // rows per lane in the product phase
     // terms a 64-bit accumulator may take before a Montgomery reduction: sum < q * 2^32
@@ -571,7 +612,12 @@ template <int SET, int RING, bool REC = false> struct NussWarp {
         uint32_t x[32], y[32];
 #pragma unroll
         for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
-        if (REC) {
+        if (F64) {
+            uint32_t zz[32];
+            NussRowF64<SET>::product(x, y, zz);
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) xr[j] = zz[j];
+        } else if (REC) {
             // same output convention as the schoolbook branches below: LAZYQ — product * 2^-(LOGM+1) in
             // [-q/2, 3q/2); canonical — product * 2^-32 in [0, q)
             constexpr uint32_t EXTRA = LAZYQ ? c_powmod((Q + 1) / 2, LOGM + 1, Q) : c_powmod(T::C::R_MODQ, Q - 2, Q);
@@ -647,10 +693,10 @@ template <int SET, int RING, bool REC = false> struct NussWarp {
     }
 };
 
-template <int SET, int RING, bool REC = false>
-__global__ void __launch_bounds__(NussWarp<SET, RING, REC>::WARPS * 32)
+template <int SET, int RING, int MODE = 0>
+__global__ void __launch_bounds__(NussWarp<SET, RING, MODE>::WARPS * 32)
 k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
-    using W = NussWarp<SET, RING, REC>;
+    using W = NussWarp<SET, RING, MODE>;
     using K = NussCfg<SET>;
     using O = typename W::O;
     using T = Tile<SET>;
@@ -681,6 +727,13 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
 #pragma unroll
             for (uint32_t i = 0; i < K::M; i++) v[i + K::M] = v[i];  // rows m..2m-1 are copies (NTT.cu:187-191)
             W::forward(v, lane);
+            if constexpr (W::F64) {
+                // FP64 row products take operands in [-q/2, 3q/2); x also takes 2^-(LOGM+1), the halvings of the inverse stages
+                const TwPair one{1u, T::C::MU32}, halves = tw_signed_c(c_powmod((T::Q + 1) / 2, K::LOGM + 1, T::Q), T::Q);
+                const TwPair sw{op ? one.w : halves.w, op ? one.ws : halves.ws};
+#pragma unroll
+                for (uint32_t r = 0; r < W::ROWS; r++) v[r] = T::smul_shoup(v[r], sw);
+            }
             uint32_t* s = op ? sy : sx;
 #pragma unroll
             for (uint32_t r = 0; r < W::ROWS; r++) s[r * W::RS + lane] = v[r];
@@ -717,7 +770,11 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
 #ifndef QT_NUSS_AUTO_RECURSIVE
 #define QT_NUSS_AUTO_RECURSIVE 1
 #endif
-enum : int { NUSS_AUTO = 0, NUSS_SCHOOLBOOK = 1, NUSS_RECURSIVE = 2 };
+#ifndef QT_NUSS_AUTO_F64
+#define QT_NUSS_AUTO_F64 1
+#endif
+enum : int { NUSS_AUTO = 0, NUSS_SCHOOLBOOK = 1, NUSS_RECURSIVE = 2, NUSS_FP64 = 3 };
+template <int SET> constexpr bool nuss_has_f64() { return NussCfg<SET>::R == 32 && NussRowF64<SET>::OK; }
 
 template <class Kern> int nuss_prepare(Kern k, int threads, size_t smem, int* occ_min) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -733,10 +790,15 @@ template <int SET> int nuss_setup(int num_sms, int* grid) {
     using K = NussCfg<SET>;
     int occ = 64, rc = 0;
     if constexpr (K::R == 32) {  // warp-resident kernels
-        using W = NussWarp<SET, 0>;  // every variant has the same CTA shape
-        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 0, false>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
-        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, false>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
-        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, true>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+        using W = NussWarp<SET, 0>;
+        using WR = NussWarp<SET, 1, 1>;
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 0, 0>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 0>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 1>, WR::WARPS * 32, WR::SMEM_BYTES, &occ))) return rc;
+        if constexpr (nuss_has_f64<SET>()) {
+            using WF = NussWarp<SET, 1, 2>;
+            if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 2>, WF::WARPS * 32, WF::SMEM_BYTES, &occ))) return rc;
+        }
     } else {
         if ((rc = nuss_prepare(k_nussbaumer<SET, 0, false>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
         if ((rc = nuss_prepare(k_nussbaumer<SET, 1, false>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
@@ -750,14 +812,19 @@ template <int SET>
 int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring, int variant,
                 cudaStream_t s) {
     using K = NussCfg<SET>;
-    const bool rec = ring == 1 && (variant == NUSS_RECURSIVE || (variant == NUSS_AUTO && QT_NUSS_AUTO_RECURSIVE));
+    const bool f64 = ring == 1 && nuss_has_f64<SET>() && (variant == NUSS_FP64 || (variant == NUSS_AUTO && QT_NUSS_AUTO_F64));
+    const bool rec = ring == 1 && !f64 && (variant == NUSS_RECURSIVE || (variant == NUSS_AUTO && QT_NUSS_AUTO_RECURSIVE));
+    if (variant == NUSS_FP64 && ring == 1 && !nuss_has_f64<SET>()) return -4;  // QT_ERR_UNSUPPORTED
     if constexpr (K::R == 32) {
         if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15) != 0) return -2;  // 128-bit accesses
         using W = NussWarp<SET, 0>;
         const int g = (int)(batch < (size_t)max_grid ? batch : (size_t)max_grid);  // small batches spread over all SMs
-        if (ring == 0) k_nussbaumer_warp<SET, 0, false><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
-        else if (rec) k_nussbaumer_warp<SET, 1, true><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
-        else k_nussbaumer_warp<SET, 1, false><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        if (ring == 0) k_nussbaumer_warp<SET, 0, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        else if (f64) {
+            if constexpr (nuss_has_f64<SET>())
+                k_nussbaumer_warp<SET, 1, 2><<<g, NussWarp<SET, 1, 2>::WARPS * 32, NussWarp<SET, 1, 2>::SMEM_BYTES, s>>>(x, y, z, batch);
+        } else if (rec) k_nussbaumer_warp<SET, 1, 1><<<g, NussWarp<SET, 1, 1>::WARPS * 32, NussWarp<SET, 1, 1>::SMEM_BYTES, s>>>(x, y, z, batch);
+        else k_nussbaumer_warp<SET, 1, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
         return (int)cudaGetLastError();
     } else {
         const size_t groups = (batch + K::P - 1) / K::P;

@@ -170,7 +170,8 @@ class Engine:
         _check(lib().qt_set_fused_variant(self._h, variant))
 
     def set_nussbaumer_variant(self, variant):
-        """row products of the Z_q Nussbaumer kernels: 0 automatic, 1 schoolbook, 2 recursive (split once more)"""
+        """row products of the Z_q Nussbaumer kernels: 0 automatic, 1 schoolbook, 2 recursive (split once more),
+        3 schoolbook on the FP64 pipe (q < 2^25)"""
         _check(lib().qt_set_nussbaumer_variant(self._h, variant))
 
     def synchronize(self):

@@ -335,6 +335,17 @@ template <int SET> int emu_inner_lazy(const uint32_t* x, const uint32_t* y, uint
     return 0;
 }
 
+// NussRowF64 (row products on the FP64 pipe) on operands in [-q/2, 3q/2)
+template <int SET> int emu_row_f64(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t rows) {
+    for (size_t r = 0; r < rows; r++) {
+        uint32_t xa[32], ya[32], za[32];
+        for (int j = 0; j < 32; j++) { xa[j] = x[32 * r + j]; ya[j] = y[32 * r + j]; }
+        NussRowF64<SET>::product(xa, ya, za);
+        for (int j = 0; j < 32; j++) z[32 * r + j] = za[j];
+    }
+    return 0;
+}
+
 #define EMU_DISPATCH(set, call)                  \
     switch (set) {                               \
     case SET_I: emu<SET_I>().call; break;        \
@@ -397,6 +408,13 @@ int qtemu_inner_lazy(int set, const uint32_t* x, const uint32_t* y, uint32_t* z,
     switch (set) {
     case SET_I: return emu_inner_lazy<SET_I>(x, y, z, rows);
     case SET_III: return emu_inner_lazy<SET_III>(x, y, z, rows);
+    default: return -1;
+    }
+}
+int qtemu_row_f64(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t rows) {
+    switch (set) {
+    case SET_I: return emu_row_f64<SET_I>(x, y, z, rows);
+    case SET_III: return emu_row_f64<SET_III>(x, y, z, rows);
     default: return -1;
     }
 }

@@ -29,6 +29,7 @@ def emu():
     L.qtemu_nussbaumer.argtypes = [C.c_int, u, u, u, C.c_size_t, C.c_int]
     L.qtemu_nussbaumer_recursive.argtypes = [C.c_int, u, u, u, C.c_size_t]
     L.qtemu_inner_lazy.argtypes = [C.c_int, u, u, u, C.c_size_t]
+    L.qtemu_row_f64.argtypes = [C.c_int, u, u, u, C.c_size_t]
     return L
 
 
@@ -169,3 +170,29 @@ def test_inner_lazy_product_ranges(emu, oracle, s):
     assert zs.min() >= -(q // 2) - 1 and zs.max() < 3 * q // 2 + 1
     assert np.array_equal(zs % q, _negacyclic_rows(x, y, q))
     assert zs[5, 0] % q == q - 1
+
+
+@pytest.mark.parametrize("s", [SET_I, SET_III])
+def test_fp64_row_product_exact(emu, oracle, s):
+    """NussRowF64: operands anywhere in [-q/2, 3q/2) incl. the extremes with every term of one sign (the largest
+    partial sums, 72 q^2 < 2^53); the double-precision accumulation must be exact and |z| <= q/2 + 1."""
+    q = oracle.params(s).q
+    lo, hi = -(q // 2), (3 * q) // 2 - 1
+    rng = np.random.default_rng(40 + s)
+    rows = 24
+    x = rng.integers(lo, hi + 1, (rows, 32), dtype=np.int64)
+    y = rng.integers(lo, hi + 1, (rows, 32), dtype=np.int64)
+    k = np.arange(32)
+    x[0, :] = hi; y[0, :] = hi                       # output 31: 32 terms of +hi^2
+    x[1, :] = hi; y[1, :] = np.where(k % 2 == 0, hi, lo)
+    x[2, :] = lo; y[2, :] = hi
+    x[3, :] = hi; y[3, :] = hi; x[3, 16:] = 0        # partial wrap
+    x[4, :] = 0
+    x[5, :] = 0; x[5, 31] = 1; y[5, :] = 0; y[5, 1] = 1
+    xu = x.astype(np.int32).view(np.uint32).ravel().copy()
+    yu = y.astype(np.int32).view(np.uint32).ravel().copy()
+    z = np.zeros_like(xu)
+    assert emu.qtemu_row_f64(s, _p(xu), _p(yu), _p(z), rows) == 0
+    zs = z.view(np.int32).astype(np.int64).reshape(rows, 32)
+    assert np.abs(zs).max() <= q // 2 + 1
+    assert np.array_equal(zs % q, _negacyclic_rows(x, y, q))

@@ -361,11 +361,15 @@ def test_nussbaumer_ring_other_sizes(engines, oracle, golden, qt, s):
     assert sha(z0) == golden[name + "_ring_schoolbook_b1_sha256"]
 
 
-@pytest.mark.parametrize("nv", [0, 1, 2])  # row products: automatic, schoolbook, recursive
+@pytest.mark.parametrize("nv", [0, 1, 2, 3])  # row products: automatic, schoolbook, recursive, FP64 pipe
 @pytest.mark.parametrize("s", ALL_SETS)
 def test_nussbaumer_modq_equals_ntt(engines, oracle, qt, s, nv):
     import torch
     eng = engines[s]
+    if nv == 3 and eng.q >= 1 << 25:
+        with pytest.raises(qt.QtError):      # FP64 row products need q < 2^25
+            eng.set_nussbaumer_variant(3)
+        return
     B = 9
     n, q = eng.n, eng.q
     x, y = rand_pair(q, B * n, 555 + s)
@@ -397,7 +401,7 @@ def test_nussbaumer_row_variants_agree_at_size(engines, oracle, qt, s):
     x, y = rand_pair(q, B * n, 777 + s)
     tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda()
     outs = {}
-    for nv in (1, 2):
+    for nv in (1, 2) + ((3,) if q < 1 << 25 else ()):
         tz = torch.empty_like(tx)
         eng.set_nussbaumer_variant(nv)
         try:
@@ -411,12 +415,13 @@ def test_nussbaumer_row_variants_agree_at_size(engines, oracle, qt, s):
         finally:
             eng.set_nussbaumer_variant(0)
     assert np.array_equal(outs[1], outs[2])
+    assert 3 not in outs or np.array_equal(outs[1], outs[3])
     assert np.array_equal(outs[("ring", 1)], outs[("ring", 2)])
     k = 40 * n
     assert np.array_equal(outs[2][:k], oracle.polymul(s, x[:k], y[:k]))
     assert np.array_equal(outs[2][-k:], oracle.polymul(s, x[-k:], y[-k:]))
     with pytest.raises(qt.QtError):
-        eng.set_nussbaumer_variant(3)
+        eng.set_nussbaumer_variant(4)
 
 
 def test_cxx_harness_reference_command_line():

@@ -26,8 +26,13 @@ for name in args.sets.split(","):
     with torch.cuda.stream(stream):
         eng.fill_uniform(x, 1, 0); eng.fill_uniform(y, 2, 0)
     ref = None
-    for label, ring, nv in (("ring 2^32-1", 0, 0), ("Z_q schoolbook rows", 1, 1), ("Z_q recursive rows", 1, 2)):
-        eng.set_nussbaumer_variant(nv)
+    for label, ring, nv in (("ring 2^32-1", 0, 0), ("Z_q schoolbook rows", 1, 1), ("Z_q recursive rows", 1, 2),
+                            ("Z_q FP64-pipe rows", 1, 3), ("Z_q automatic", 1, 0)):
+        try:
+            eng.set_nussbaumer_variant(nv)
+        except qt.QtError as ex:
+            print(f"{name:6s} {label:22s}: {ex}", flush=True)
+            continue
         with torch.cuda.stream(stream):
             for _ in range(2): eng.nussbaumer(x, y, z, ring, B)
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
