@@ -269,21 +269,45 @@ template <int SET> struct NussRowF64 {
     using T = Tile<SET>;
     static constexpr uint32_t Q = Cfg<SET>::Q;
     static constexpr bool OK = T::LAZY && 72.0 * (double)Q * (double)Q < 9007199254740992.0;
-    // z = x (*) y mod (w^32 + 1, q) for two's-complement x, y in [-q/2, 3q/2); z in [-q/2 - 1, q/2 + 1]
-    static QT_HD void product(const uint32_t (&x)[32], const uint32_t (&y)[32], uint32_t (&z)[32]) {
-        double xd[32], yd[32];
+    // z = x (*) y mod (w^32 + 1, q) for two's-complement x, y in [-q/2, 3q/2); z in [-q/2 - 1, q/2 + 1].
+    // xr, yr are the rows where they lie (shared memory); z overwrites x.  Outer-product order — step j multiplies
+    // x_j into all accumulators, so consecutive DFMAs are independent — in two halves of 16 outputs: y (64
+    // registers) + 16 accumulators (32) stay live instead of y + 32 accumulators, x_j is loaded and converted
+    // when its step comes (twice in total).  The __syncwarp between the halves keeps the compiler from merging
+    // them again.
+    static QT_HD void product(uint32_t* xr, const uint32_t* yr) {
+        double yd[32];
 #pragma unroll
-        for (uint32_t j = 0; j < 32; j++) { xd[j] = (double)(int32_t)x[j]; yd[j] = (double)(int32_t)y[j]; }
+        for (uint32_t j = 0; j < 32; j++) yd[j] = (double)(int32_t)yr[j];
         const double INVQ = 1.0 / (double)Q, QD = (double)Q, MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+        uint32_t z0[16];
 #pragma unroll
-        for (uint32_t k = 0; k < 32; k++) {
-            double acc = 0.0;
+        for (uint32_t h = 0; h < 2; h++) {
+            double acc[16];
 #pragma unroll
-            for (uint32_t j = 0; j < 32; j++)  // wrapped terms enter negated
-                acc = (j <= k) ? fma(xd[j], yd[(k - j) & 31], acc) : fma(-xd[j], yd[(32 + k - j) & 31], acc);
-            const double t = fma(acc, INVQ, MAGIC) - MAGIC;  // rint(acc / q)
-            z[k] = (uint32_t)(int32_t)fma(-t, QD, acc);
+            for (uint32_t kk = 0; kk < 16; kk++) acc[kk] = 0.0;
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) {
+                const double xd = (double)(int32_t)xr[j];
+#pragma unroll
+                for (uint32_t kk = 0; kk < 16; kk++) {  // wrapped terms enter negated
+                    const uint32_t k = 16 * h + kk;
+                    acc[kk] = (j <= k) ? fma(xd, yd[(k - j) & 31], acc[kk]) : fma(-xd, yd[(32 + k - j) & 31], acc[kk]);
+                }
+            }
+#pragma unroll
+            for (uint32_t kk = 0; kk < 16; kk++) {
+                const double t = fma(acc[kk], INVQ, MAGIC) - MAGIC;  // rint(acc / q)
+                const uint32_t r = (uint32_t)(int32_t)fma(-t, QD, acc[kk]);
+                if (h == 0) z0[kk] = r;
+                else xr[16 + kk] = r;
+            }
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
         }
+#pragma unroll
+        for (uint32_t kk = 0; kk < 16; kk++) xr[kk] = z0[kk];
     }
 };
 
@@ -548,7 +572,7 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
     // (two 8x8 row blocks live at once): 8 warps with up to 255 registers measured faster for the 64-row sets
     // (qTESLA-III 78.5 vs 74.6 M polymul/s, p-I 57.7 vs 53.1; qTESLA-I, 32 rows: 182.8 vs 189.7).
 #ifndef QT_NUSS_F64_WARPS
-#define QT_NUSS_F64_WARPS 8  // 183 / 221 registers without spills; 12 warps (168 registers, 240 B spilled): 75.7 vs 81.6 M polymul/s
+#define QT_NUSS_F64_WARPS 12  // 158 / 168 registers, no spills (8 warps: 78.6 vs 87.0 M polymul/s at n=1024)
 #endif
     static constexpr uint32_t WARPS = F64 ? QT_NUSS_F64_WARPS : (REC && ROWS == 64) ? 8 : QT_NUSS_WARPS;
     static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_WORDS * sizeof(uint32_t);
@@ -609,15 +633,14 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
 
     // one row: z = x (*) y negacyclic, length 32; x, y, z are shared-memory rows (z overwrites x)
     static __device__ __forceinline__ void product_row(uint32_t* xr, const uint32_t* yr) {
+        if constexpr (F64) {
+            NussRowF64<SET>::product(xr, yr);
+            return;
+        }
         uint32_t x[32], y[32];
 #pragma unroll
         for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
-        if (F64) {
-            uint32_t zz[32];
-            NussRowF64<SET>::product(x, y, zz);
-#pragma unroll
-            for (uint32_t j = 0; j < 32; j++) xr[j] = zz[j];
-        } else if (REC) {
+        if (REC) {
             // same output convention as the schoolbook branches below: LAZYQ — product * 2^-(LOGM+1) in
             // [-q/2, 3q/2); canonical — product * 2^-32 in [0, q)
             constexpr uint32_t EXTRA = LAZYQ ? c_powmod((Q + 1) / 2, LOGM + 1, Q) : c_powmod(T::C::R_MODQ, Q - 2, Q);

@@ -338,10 +338,10 @@ template <int SET> int emu_inner_lazy(const uint32_t* x, const uint32_t* y, uint
 // NussRowF64 (row products on the FP64 pipe) on operands in [-q/2, 3q/2)
 template <int SET> int emu_row_f64(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t rows) {
     for (size_t r = 0; r < rows; r++) {
-        uint32_t xa[32], ya[32], za[32];
+        uint32_t xa[32], ya[32];
         for (int j = 0; j < 32; j++) { xa[j] = x[32 * r + j]; ya[j] = y[32 * r + j]; }
-        NussRowF64<SET>::product(xa, ya, za);
-        for (int j = 0; j < 32; j++) z[32 * r + j] = za[j];
+        NussRowF64<SET>::product(xa, ya);  // z over x
+        for (int j = 0; j < 32; j++) z[32 * r + j] = xa[j];
     }
     return 0;
 }
