@@ -94,6 +94,12 @@ int qt_set_fused_variant(qt_ctx* ctx, int variant);
  * 3 = schoolbook on the FP64 pipe with exact double-precision accumulation (q < 2^25 only, else
  * QT_ERR_UNSUPPORTED).  Results are identical; the ring 2^32-1 always uses the reference's schoolbook order. */
 int qt_set_nussbaumer_variant(qt_ctx* ctx, int variant);
+/* Programmatic dependent launch of the TMA-staged kernels: the set-up of a launch (barriers, twiddle table) overlaps
+ * the tail of the previous kernel of the stream; operands are touched only after that kernel has completed.
+ * 0 = automatic: on when the ctx stream is a non-blocking stream (the own stream; a torch side stream), off on the
+ * legacy default stream and other blocking streams, whose implicit ordering against the default stream the early
+ * launch is not documented to keep; 1 = never; 2 = always. */
+int qt_set_launch_overlap(qt_ctx* ctx, int mode);
 int qt_device_malloc(qt_ctx* ctx, size_t bytes, void** out_dev);
 int qt_device_free(qt_ctx* ctx, void* dev);
 /* pinned host memory for the host-pointer entry points */

@@ -49,6 +49,9 @@ struct qt_ctx {
     bool split_ok = false;
     int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged, 3 split tile (n=2048)
     int nuss_variant = 0;  // 0 auto, 1 schoolbook row products, 2 recursive row products (Z_q)
+    int overlap = 0;       // programmatic dependent launch: 0 auto (non-blocking streams only), 1 never, 2 always
+    cudaStream_t overlap_probe = nullptr;  // stream the cached answer below belongs to
+    bool overlap_ok = false, overlap_probed = false;
     size_t smem_fused = 0, smem_one = 0, smem_tma = 0;
     std::atomic<uint64_t> launches{0};
     // host pipeline (qt_polymul_host): lazily created
@@ -185,18 +188,52 @@ inline int grid_for(int max_grid, size_t tiles) {
     return (int)std::max<size_t>(1, std::min<size_t>((size_t)max_grid, ctas));
 }
 
+// Launch of a kernel that contains pdl_wait() (qt_kernels.cuh) with programmatic stream serialization: its
+// prologue may overlap the tail of the previous kernel of the stream.  Only such kernels may be launched this way.
+// "Automatic" enables it on non-blocking streams only: a blocking stream is implicitly ordered against the legacy
+// default stream, an ordering the early launch is not documented to keep.
+static bool overlap_allowed(qt_ctx* c, cudaStream_t s) {
+    if (!QT_PDL || c->overlap == 1) return false;
+    if (c->overlap == 2) return true;
+    if (!c->overlap_probed || c->overlap_probe != s) {
+        unsigned flags = 0;
+        c->overlap_ok = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+                        cudaStreamGetFlags(s, &flags) == cudaSuccess && (flags & cudaStreamNonBlocking) != 0;
+        (void)cudaGetLastError();
+        c->overlap_probe = s;
+        c->overlap_probed = true;
+    }
+    return c->overlap_ok;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(qt_ctx* c, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = overlap_allowed(c, s) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B,
                                       cudaStream_t s) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;  // bulk copies need 16-byte alignment
     const bool tma = c->occ_tma > 0 && aligned && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
-    if (SET == SET_P_III && c->split_ok && aligned && (c->variant == 3 || c->variant == 0))
-        k_polymul_split<0><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B)),
-                          SplitShape::WARPS * 32, SplitShape::SMEM, s>>>(x, y, z, B, c->d_tab_split);
-    else if (tma)
-        k_polymul_tma<SET><<<(int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, tiles)),
-                             TmaCfg<SET>::WARPS * 32, c->smem_tma, s>>>(
-            x, y, z, B, c->d_tab[1]);
+    if (SET == SET_P_III && c->split_ok && aligned && (c->variant == 3 || c->variant == 0)) {
+        cudaError_t e = launch_pdl(c, k_polymul_split<0>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B)),
+                                   SplitShape::WARPS * 32, SplitShape::SMEM, s, x, y, z, B, c->d_tab_split);
+        if (e != cudaSuccess) return (int)e;
+    } else if (tma) {
+        cudaError_t e = launch_pdl(c, k_polymul_tma<SET>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, tiles)),
+                                   TmaCfg<SET>::WARPS * 32, c->smem_tma, s, x, y, z, B, c->d_tab[1]);
+        if (e != cudaSuccess) return (int)e;
+    }
     else
         k_polymul<SET><<<grid_for(c->grid_fused, tiles), WARPS_PER_CTA * 32, c->smem_fused, s>>>(
             x, y, z, B, c->d_tab[1]);
@@ -209,27 +246,31 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
     if ((((uintptr_t)ahat | (uintptr_t)y) & 15) != 0) return QT_ERR_BAD_ARG;  // 128-bit / bulk-copy alignment
     if (SET == SET_P_III && c->split_ok && c->variant != 2) {
         const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B));
-        if (bcast) k_polymul_split<1><<<g, SplitShape::WARPS * 32, SplitShape::SMEM_BCAST, c->stream>>>(ahat, y, z, B, c->d_tab_split);
-        else k_polymul_split<2><<<g, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream>>>(ahat, y, z, B, c->d_tab_split);
+        const cudaError_t e = bcast ? launch_pdl(c, k_polymul_split<1>, g, SplitShape::WARPS * 32, SplitShape::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab_split)
+                                    : launch_pdl(c, k_polymul_split<2>, g, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, ahat, y, z, B, c->d_tab_split);
+        if (e != cudaSuccess) return (int)e;
         c->launches++;
         return (int)cudaGetLastError();
     }
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
-    if (bcast) k_polymul_ntt<SET, true><<<grid, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM_BCAST, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
-    else k_polymul_ntt<SET, false><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(ahat, y, z, B, c->d_tab[1]);
+    const cudaError_t e = bcast ? launch_pdl(c, k_polymul_ntt<SET, true>, grid, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab[1])
+                                : launch_pdl(c, k_polymul_ntt<SET, false>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, ahat, y, z, B, c->d_tab[1]);
+    if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <int SET, bool INV> int launch_ntt_tma(qt_ctx* c, uint32_t* a, size_t B) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
-    k_ntt_tma<SET, INV><<<grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream>>>(a, B, c->d_tab[0]);
+    const cudaError_t e = launch_pdl(c, k_ntt_tma<SET, INV>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, a, B, c->d_tab[0]);
+    if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <bool INV> int launch_ntt_split(qt_ctx* c, uint32_t* a, size_t B) {
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, B));
-    k_ntt_split<INV><<<grid, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream>>>(a, B, c->d_tab_split);
+    const cudaError_t e = launch_pdl(c, k_ntt_split<INV>, grid, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, a, B, c->d_tab_split);
+    if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -464,6 +505,12 @@ int qt_set_fused_variant(qt_ctx* c, int variant) {
     if (variant == 2 && c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
     if (variant == 3 && !c->split_ok) return QT_ERR_UNSUPPORTED;
     c->variant = variant;
+    return 0;
+}
+
+int qt_set_launch_overlap(qt_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return QT_ERR_BAD_ARG;
+    c->overlap = mode;
     return 0;
 }
 

@@ -24,6 +24,26 @@ constexpr int WARPS_PER_CTA = 8;   // direct-load kernels
 #endif
 
 // launch geometry of the TMA-staged fused kernel per parameter set
+// Programmatic dependent launch (QT_PDL): the TMA-staged kernels let the NEXT launch of the stream start its CTAs
+// as soon as this grid's CTAs leave their SMs (pdl_launch_dependents at the top); everything a kernel does before
+// pdl_wait() touches only shared memory and the constant twiddle table, so barrier set-up and the table copy
+// overlap the tail of the previous launch.  pdl_wait() returns when the previous grid has completed and its
+// writes are visible; it is a no-op for a launch without the attribute.  Measured (run r01s): n=1024 batch 65 536
+// 240.8 -> 244.5 M polymul/s, batch 1 024 10.3 -> 7.5 us per launch.
+#ifndef QT_PDL
+#define QT_PDL 1
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if QT_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if QT_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 template <int SET> struct TmaCfg {
     static constexpr int WARPS = (Cfg<SET>::E == 64) ? QT_TMA_WARPS_E64 : QT_TMA_WARPS;
     static constexpr int MINB = (Cfg<SET>::E == 64) ? 1 : QT_TMA_MINB;  // 64 coefficients per thread need the registers
@@ -174,17 +194,19 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
         }
     };
 
+    pdl_launch_dependents();
     if (lane == 0) {
         mbar_init(bar_a, 1);
         mbar_init(bar_b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        if (tile < ntiles) {
-            issue(x, A, bar_a, tile);
-            issue(y, B, bar_b, tile);
-        }
     }
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    pdl_wait();  // the operands may be the previous launch's output
+    if (lane == 0 && tile < ntiles) {
+        issue(x, A, bar_a, tile);
+        issue(y, B, bar_b, tile);
+    }
     __syncthreads();
 
     const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
@@ -272,17 +294,19 @@ k_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
         mbar_expect_tx(bar, G::WORDS * (uint32_t)sizeof(uint32_t));
         bulk_g2s(st, g + t * G::WORDS, G::WORDS * (uint32_t)sizeof(uint32_t), bar);
     };
+    pdl_launch_dependents();
     if (lane == 0) {
         mbar_init(bar_a, 1);
         mbar_init(bar_b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        if (tile < batch) {
-            if (MODE == 0) issue(x, A, bar_a, tile);
-            issue(y, B, bar_b, tile);
-        }
     }
     copy_table_to_smem(s_tw, g_lane, T::TABLE_QUADS);
+    pdl_wait();  // the operands may be the previous launch's output
+    if (lane == 0 && tile < batch) {
+        if (MODE == 0) issue(x, A, bar_a, tile);
+        issue(y, B, bar_b, tile);
+    }
     // MODE 1: the one a_hat stays in shared memory (behind the barriers), each half in the half tile's
     // swizzled cols layout
     uint32_t* s_ahat = reinterpret_cast<uint32_t*>(s_bar + 2 * NW);
@@ -403,14 +427,16 @@ k_ntt_split(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
         mbar_expect_tx(bar, G::WORDS * (uint32_t)sizeof(uint32_t));
         bulk_g2s(st, a + t * G::WORDS, G::WORDS * (uint32_t)sizeof(uint32_t), bar);
     };
+    pdl_launch_dependents();
     if (lane == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        if (tile < batch) issue(buf0, bar0, tile);
     }
     copy_table_to_smem(s_tw, g_lane, T::TABLE_QUADS);
+    pdl_wait();
+    if (lane == 0 && tile < batch) issue(buf0, bar0, tile);
     __syncthreads();
     for (uint32_t k = 0; tile < batch; tile += stride, k++) {
         uint32_t* st = buf0 + (k & 1) * G::WORDS;
@@ -512,13 +538,15 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
                 bulk_g2s(st + p * G::POLY_STRIDE, y + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar);
         }
     };
+    pdl_launch_dependents();
     if (lane == 0) {
         mbar_init(bar0, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        if (tile < ntiles) issue(B, bar0, tile);
     }
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    pdl_wait();  // y and a_hat may be the previous launch's output
+    if (lane == 0 && tile < ntiles) issue(B, bar0, tile);
     // BCAST: the one a_hat lives in shared memory for the whole kernel (behind the barriers), stored with
     // the tile's swizzle so that the 128-bit reads below are conflict-free
     uint32_t* s_ahat = reinterpret_cast<uint32_t*>(s_bar + 2 * NW);
@@ -714,14 +742,16 @@ k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
                 bulk_g2s(st + p * G::POLY_STRIDE, a + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar);
         }
     };
+    pdl_launch_dependents();
     if (lane == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        if (tile < ntiles) issue(buf0, bar0, tile);
     }
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    pdl_wait();
+    if (lane == 0 && tile < ntiles) issue(buf0, bar0, tile);
     __syncthreads();
     const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     for (uint32_t k = 0; tile < ntiles; tile += stride, k++) {

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "qt_synchronize": (C.c_int, [_vp]),
     "qt_set_fused_variant": (C.c_int, [_vp, C.c_int]),
     "qt_set_nussbaumer_variant": (C.c_int, [_vp, C.c_int]),
+    "qt_set_launch_overlap": (C.c_int, [_vp, C.c_int]),
     "qt_device_malloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "qt_device_free": (C.c_int, [_vp, _vp]),
     "qt_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
@@ -169,6 +170,10 @@ class Engine:
         """0 automatic, 1 direct coalesced loads, 2 TMA bulk copies staged through shared memory"""
         _check(lib().qt_set_fused_variant(self._h, variant))
 
+    def set_launch_overlap(self, mode):
+        """programmatic dependent launch of the TMA-staged kernels: 0 automatic (non-blocking streams), 1 never, 2 always"""
+        _check(lib().qt_set_launch_overlap(self._h, mode))
+
     def set_nussbaumer_variant(self, variant):
         """row products of the Z_q Nussbaumer kernels: 0 automatic, 1 schoolbook, 2 recursive (split once more),
         3 schoolbook on the FP64 pipe (q < 2^25)"""
@@ -247,6 +252,7 @@ class Engine:
         import torch
         dev = torch.device("cuda", self.device)
         ts = [torch.from_numpy(np.ascontiguousarray(a, np.uint32).view(np.int32)).to(dev) for a in host_arrays]
+        torch.cuda.current_stream(dev).synchronize()  # the engine's stream is not ordered against torch's
         out = fn(*ts)
         self.synchronize()
         torch.cuda.synchronize(dev)

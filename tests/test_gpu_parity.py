@@ -22,8 +22,16 @@ def sha(a):
 def engines(qt):
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    # ONE stream for torch and the engines: the tests interleave torch device ops (copy_, clone) with engine
+    # calls, and an engine's own stream is non-blocking, i.e. not ordered against torch's default stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     es = {s: qt.Engine(s, 0) for s in ALL_SETS}
+    for e in es.values():
+        e.set_stream(stream.cuda_stream)
     yield es
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())
     for e in es.values():
         e.close()
 
@@ -307,6 +315,38 @@ def test_full_size_properties(engines, oracle, s):
     idx = [0, 1, B // 2, B - 2, B - 1]
     pick = lambda t: np.concatenate([t[i * n:(i + 1) * n].cpu().numpy().view(np.uint32) for i in idx])
     assert np.array_equal(pick(z), oracle.polymul(s, pick(x), pick(y)))
+
+
+@pytest.mark.parametrize("mode", [1, 2])  # programmatic dependent launch: never / always
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_dependent_launch_chains(engines, oracle, s, mode):
+    """Back-to-back launches on one stream in which every launch consumes the previous launch's output — the case
+    programmatic dependent launch must keep ordered (operands are touched only after griddepcontrol.wait)."""
+    import torch
+    eng = engines[s]
+    n, q = eng.n, eng.q
+    eng.set_launch_overlap(mode)
+    try:
+        for B in (5, 300, 9000):
+            x, y = rand_pair(q, B * n, 900 + s + B)
+            tx = torch.from_numpy(x.view(np.int32)).cuda(); ty = torch.from_numpy(y.view(np.int32)).cuda()
+            t1 = torch.empty_like(tx); t2 = torch.empty_like(tx); t3 = torch.empty_like(tx)
+            for _ in range(3):                       # repeated: the launches of one round overlap the previous round's tail
+                eng.polymul(tx, ty, t1)              # t1 = x y
+                eng.polymul(t1, ty, t2)              # t2 = x y^2
+                eng.polymul(t2, t1, t3)              # t3 = x^2 y^3
+                t4 = t3.clone()
+                eng.ntt_forward(t4); eng.ntt_inverse(t4)          # round trip of a fresh output
+                ah = t1[:n].clone(); eng.ntt_forward(ah, 1)
+                t5 = torch.empty_like(tx)
+                eng.polymul_ntt(ah, t3, t5, True)    # cached transform of the first polynomial of t1, broadcast
+            eng.synchronize()
+            r1 = oracle.polymul(s, x, y); r2 = oracle.polymul(s, r1, y); r3 = oracle.polymul(s, r2, r1)
+            assert np.array_equal(t3.cpu().numpy().view(np.uint32), r3)
+            assert np.array_equal(t4.cpu().numpy().view(np.uint32), r3)
+            assert np.array_equal(t5.cpu().numpy().view(np.uint32), oracle.polymul(s, np.tile(r1[:n], B), r3))
+    finally:
+        eng.set_launch_overlap(0)
 
 
 def test_nussbaumer_ring_equals_oracle(engines, oracle, qt):
