@@ -19,6 +19,12 @@
 //     no communication at all (IMAD.WIDE back to back);
 //   * __syncthreads only between phases.
 // The phase functions are __host__ __device__ so tests/emu can run them thread by thread.
+//
+// Kernels: k_nussbaumer (the mapping above; n = 2048) and k_nussbaumer_warp (one warp per polynomial, rows in
+// registers, rotations as warp shuffles; n = 512, 1024).  Row products of the Z_q kernels come in three
+// bit-identical forms (qt_set_nussbaumer_variant): schoolbook on the integer pipe, recursive (NussInner: the
+// row product split once more) and schoolbook on the FP64 pipe with exact double-precision accumulation
+// (NussRowF64, q < 2^25).
 #pragma once
 #include <cmath>
 #include <cstddef>
