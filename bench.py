@@ -250,6 +250,8 @@ def main():
     ap.add_argument("--set", default="III", choices=list(SETS))
     ap.add_argument("--batch", type=int, default=0, help="polynomials per GPU per step (default: BASELINE config)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other parameter sets / CPU baseline")
+    ap.add_argument("--launch-overlap", type=int, default=0, choices=[0, 1, 2],
+                    help="programmatic dependent launch of the fused kernel: 0 automatic (on), 1 never, 2 always")
     ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3],
                     help="fused-kernel data path: 0 automatic, 1 direct coalesced loads, 2 TMA-staged")
     args = ap.parse_args()
@@ -292,6 +294,7 @@ def main():
         eng.set_stream(stream.cuda_stream)
         eng.set_fused_variant(args.variant if variant is None else variant)
         eng.set_nussbaumer_variant(nuss_variant)
+        eng.set_launch_overlap(args.launch_overlap)
         step = (lambda: eng.polymul(x, y, z, batch)) if nuss_ring is None else (lambda: eng.nussbaumer(x, y, z, nuss_ring, batch))
         p = eng.params
         words = batch * p.n
@@ -495,6 +498,9 @@ def main():
             "parity_check": {"ok": parity, "polynomials_per_rank": 2 * min(512, batch // 2), "ranks_checked": world,
                              "against": "CPU oracle (oracle/qt_oracle.c)"},
             "kernel_info": eng.kernel_info(),
+            "launch": ("one fused kernel per step; stream-ordered launches without overlap" if args.launch_overlap == 1 else
+                       "one fused kernel per step, programmatic dependent launch: the barrier / twiddle-table set-up of step k+1 "
+                       "overlaps the tail of step k, operands are read only after step k has completed (qt_set_launch_overlap)"),
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
