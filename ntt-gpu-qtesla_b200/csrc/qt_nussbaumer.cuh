@@ -639,10 +639,10 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
 
     // one row: z = x (*) y negacyclic, length 32; x, y, z are shared-memory rows (z overwrites x)
     static __device__ __forceinline__ void product_row(uint32_t* xr, const uint32_t* yr) {
-        if constexpr (F64) {
-            NussRowF64<SET>::product(xr, yr);
-            return;
-        }
+        if constexpr (F64) NussRowF64<SET>::product(xr, yr);
+        else product_row_int(xr, yr);
+    }
+    static __device__ __forceinline__ void product_row_int(uint32_t* xr, const uint32_t* yr) {
         uint32_t x[32], y[32];
 #pragma unroll
         for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
