@@ -324,9 +324,13 @@ template <int SET, int RING> struct Nuss {
     static constexpr uint32_t EPL = R / 32;  // coefficients per lane in the stage phases (1 or 2)
 
     static QT_HD uint32_t brev(uint32_t x, uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+        return bits ? __brev(x) >> (32u - bits) : 0u;  // one BREV + shift instead of a run-time loop per lane
+#else
         uint32_t r = 0;
         for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
         return r;
+#endif
     }
     // rotation exponent of stage j, group i  (sr of NTT.cu:200-203)
     static QT_HD uint32_t rot(uint32_t i, uint32_t j) { return (brev(i, LOGM - j) << j) * K::ROT_UNIT; }
