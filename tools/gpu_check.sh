@@ -12,6 +12,7 @@ echo "== ubench"; timeout 120 ./tools/ubench > $OUT/ubench_$TAG.json 2>&1; timeo
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 10 --warmup 3 2>/dev/null | grep -v '^count' > $OUT/bench_ref_$TAG.json; cut -c1-300 $OUT/bench_ref_$TAG.json
 echo "== bench"; timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; tail -3 $OUT/bench_$TAG.err; cut -c1-400 $OUT/bench_$TAG.json
 echo "== sweep"; timeout 600 python tools/sweep.py > $OUT/sweep_1gpu_$TAG.jsonl 2>/dev/null; tail -3 $OUT/sweep_1gpu_$TAG.jsonl | cut -c1-300
+echo "== nussbaumer table"; timeout 200 python tools/nuss_ab.py > $OUT/nuss_ab_$TAG.log 2>&1; cat $OUT/nuss_ab_$TAG.log
 echo "== ncu launch list"
 python bench.py --steps 5 --warmup 3 --no-extras > $OUT/ncu_plain_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv \
