@@ -56,6 +56,15 @@ extern "C" {
 /* Nussbaumer rings */
 #define QT_RING_2P32M1 0 /* Z/(2^32-1): bit-exact with nussbaumer_fft (NTT.cu:167-277) */
 #define QT_RING_MODQ 1   /* Z_q: equals the NTT product, canonical */
+/* Z_q operands THROUGH the ring 2^32-1 (the sparse / small-operand path): canonical residues are
+ * centred to (-q/2, q/2], multiplied in Z/(2^32-1) by the kernel of QT_RING_2P32M1 (ring macros NTT.cu:102-134), and the
+ * signed lift of the ring value is reduced mod q.  EXACTNESS PRECONDITION: every integer coefficient of the negacyclic
+ * product of the centred operands has magnitude < 2^31 (sufficient: max_k sum_i |x~_i| |y~_(k-i)| < 2^31 — qTESLA's
+ * s*c and e*c with a small secret and a weight-h ternary challenge for every parameter set; uniform x * weight-h
+ * ternary y while h*q/2 < 2^31, i.e. any h <= 255 for qTESLA-I/III, h <= 12 for p-I, h <= 5 for p-III).  Then the
+ * result equals qt_polymul bit for bit.  The library cannot check the precondition; outside it (e.g. two uniform
+ * operands) the output is a canonical residue but NOT the Z_q product. */
+#define QT_RING_2P32M1_LIFT_Q 2
 
 typedef struct qt_ctx qt_ctx;
 
@@ -123,7 +132,8 @@ int qt_ntt_inverse(qt_ctx* ctx, uint32_t* d_a, size_t batch);
  * one launch, no scratch array; equal to qt_ntt_forward followed by qt_bitrev_copy (resp. preceded). */
 int qt_ntt_forward_natural(qt_ctx* ctx, uint32_t* d_a, size_t batch);
 int qt_ntt_inverse_natural(qt_ctx* ctx, uint32_t* d_a, size_t batch);
-/* c = a*b mod q, element-wise.  Replaces pointwise_mult (NTT.cu:1155-1160). d_c may alias. */
+/* c = a*b mod q, element-wise.  Replaces pointwise_mult (NTT.cu:1155-1160). d_c may alias.  16-byte aligned
+ * operands use 128-bit accesses; any 4-byte aligned pointer is accepted (word-wise kernel). */
 int qt_pointwise(qt_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, size_t batch);
 /* z = x*y mod (X^n+1, q), fused forward -> pointwise -> inverse in ONE launch; HBM is touched once
  * per operand.  Replaces the 31-34 launches of test_NTT_{Stockham,GS_CT,CT_CT,GS_GS,CT_GS}_nega_gpu
@@ -141,7 +151,8 @@ int qt_polymul_ntt(qt_ctx* ctx, const uint32_t* d_a_hat, int broadcast, const ui
 int qt_bitrev_copy(qt_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, size_t batch);
 /* Nussbaumer negacyclic product (NTT-free).  ring = QT_RING_2P32M1 reproduces nussbaumer_fft
  * (NTT.cu:167-277, CPU-only and single-polynomial in the reference) bit for bit, batched;
- * ring = QT_RING_MODQ runs the same structure over Z_q and equals qt_polymul. */
+ * ring = QT_RING_MODQ runs the same structure over Z_q and equals qt_polymul;
+ * ring = QT_RING_2P32M1_LIFT_Q: see the definition above (exact only under its precondition). */
 int qt_nussbaumer(qt_ctx* ctx, const uint32_t* d_x, const uint32_t* d_y, uint32_t* d_z, size_t batch,
                   int ring);
 /* synthetic operands: a[i] = splitmix64(seed + first_index + i) % q, i in [0, count) */
@@ -156,14 +167,45 @@ int qt_fill_uniform(qt_ctx* ctx, uint32_t* d_a, size_t count, uint64_t seed, uin
  * of pageable memory gives 13 GB/s).  Each of x, y, z may be of either kind.  Same role as test_NTT_*_nega_gpu (main.cuh:66-70) without the
  * fixed x=y=1 fill, the timing prints and the per-call allocation. */
 int qt_polymul_host(qt_ctx* ctx, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch);
-/* one-shot form: shards the batch contiguously over the first ngpus devices (ngpus <= 0: all),
- * one host thread + stream per device, no collective. */
+/* In-process multi-GPU form: the batch is sharded contiguously over the first ngpus devices
+ * (ngpus <= 0: all), GPU g owns polynomials [g*B/G, (g+1)*B/G); one context + one persistent host thread per
+ * device, each bound to its GPU's NUMA node; no collective, no peer access.  A handle is not thread-safe; two
+ * callers use two handles (the library keeps no process-global state). */
+typedef struct qt_multi qt_multi;
+int qt_multi_create(int param_set, int ngpus, qt_multi** out);
+int qt_multi_destroy(qt_multi* m);
+int qt_multi_gpus(qt_multi* m, int* out);
+int qt_multi_polymul_host(qt_multi* m, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch);
+/* one-shot convenience: qt_multi_create + qt_multi_polymul_host + qt_multi_destroy (pays the set-up every call) */
 int qt_polymul_host_multi(int param_set, const uint32_t* x, const uint32_t* y, uint32_t* z,
                           size_t batch, int ngpus);
-/* releases the per-device contexts qt_polymul_host_multi keeps between calls */
+/* no-op, kept for ABI compatibility (earlier versions cached per-device contexts process-wide) */
 int qt_shutdown(void);
 int qt_nussbaumer_host(qt_ctx* ctx, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
                        int ring);
+
+/* ---- CUDA graphs for launch-bound batches (no reference counterpart: the reference launches 31-34 kernels per
+ *      product from the host, NTT.cu:2127-2160).  Between qt_graph_begin and qt_graph_end the device-pointer entry
+ *      points of this context (qt_polymul, qt_polymul_ntt, qt_ntt_*, qt_pointwise, qt_bitrev_copy, qt_nussbaumer,
+ *      qt_fill_uniform, qt_memcpy_*) are RECORDED on the context's stream instead of executed; qt_graph_launch replays
+ *      the whole sequence with one host call.  The pointers and batch sizes are baked in.  The host-pointer forms
+ *      (qt_polymul_host...) and qt_synchronize must not be called while recording. ---- */
+typedef struct qt_graph qt_graph;
+int qt_graph_begin(qt_ctx* ctx);
+int qt_graph_end(qt_ctx* ctx, qt_graph** out);
+int qt_graph_launch(qt_ctx* ctx, qt_graph* graph); /* asynchronous on the ctx stream */
+int qt_graph_destroy(qt_graph* graph);
+int qt_graph_kernel_count(qt_graph* graph, uint64_t* out); /* kernels one replay launches */
+
+/* ---- host placement (no reference counterpart: the reference drives one GPU from pageable buffers,
+ *      NTT.cu:2105-2124).  Where a GPU hangs in the machine, and binding the CALLING host thread to the CPUs
+ *      of that GPU's NUMA node, so that pinned buffers the thread allocates and touches afterwards sit on the
+ *      memory controller next to the GPU's PCIe root.  Call it before qt_host_alloc / before creating the
+ *      worker threads that feed this GPU.  Unknown topology (sysfs says -1, e.g. inside a VM) is not an error:
+ *      the thread is left alone and *cpus_out = 0. ---- */
+int qt_device_pci_bus_id(int device, char* out, size_t len); /* "0000:1b:00.0", lower case; len >= 13 */
+int qt_device_numa_node(int device, int* node_out);          /* -1 when the platform does not say */
+int qt_bind_thread_to_device(int device, int* cpus_out);     /* *cpus_out = CPUs the thread is now bound to, 0 = unchanged */
 
 /* ---- introspection for benchmarks ---- */
 /* kernels launched by this context since creation (the bench's gpu_launches claim) */

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,8 @@ struct qt_ctx {
     bool overlap_ok = false, overlap_probed = false;
     size_t smem_fused = 0, smem_one = 0, smem_tma = 0;
     std::atomic<uint64_t> launches{0};
+    bool capturing = false;             // between qt_graph_begin and qt_graph_end
+    uint64_t capture_launches0 = 0;
     // host pipeline (qt_polymul_host): lazily created
     static constexpr int PIPE = 8;  // maximum number of pipeline slots
     int pipe_slots = 3;             // slots in use
@@ -85,6 +88,12 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// every entry point that touches the device: switch to the context's GPU or fail (never run on whatever device
+// happens to be current, with table pointers that belong to another one)
+#define QT_GUARD(dev)            \
+    DeviceGuard g__(dev);        \
+    if (!g__.ok) return QT_ERR_NO_DEVICE
 
 std::mutex g_uni_mutex;
 bool g_uni_uploaded[64][NUM_TILE_SETS];  // per device
@@ -192,9 +201,13 @@ inline int grid_for(int max_grid, size_t tiles) {
 // prologue may overlap the tail of the previous kernel of the stream.  Only such kernels may be launched this way.
 // "Automatic" enables it on non-blocking streams only: a blocking stream is implicitly ordered against the legacy
 // default stream, an ordering the early launch is not documented to keep.
-static bool overlap_allowed(qt_ctx* c, cudaStream_t s) {
+// `known`: OVL_YES for the streams the library creates itself (pipeline / staging streams are always non-blocking; their
+// launches come from worker threads, which must not touch the cache below), OVL_PROBE for the ctx stream, which
+// only the API caller's thread launches on.
+enum { OVL_PROBE = -1, OVL_YES = 1 };
+static bool overlap_allowed(qt_ctx* c, cudaStream_t s, int known) {
     if (!QT_PDL || c->overlap == 1) return false;
-    if (c->overlap == 2) return true;
+    if (c->overlap == 2 || known == OVL_YES) return true;
     if (!c->overlap_probed || c->overlap_probe != s) {
         unsigned flags = 0;
         c->overlap_ok = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
@@ -206,7 +219,7 @@ static bool overlap_allowed(qt_ctx* c, cudaStream_t s) {
     return c->overlap_ok;
 }
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(qt_ctx* c, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+static cudaError_t launch_pdl(qt_ctx* c, int known, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block);
@@ -214,23 +227,23 @@ static cudaError_t launch_pdl(qt_ctx* c, void (*kern)(KArgs...), int grid, int b
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = overlap_allowed(c, s) ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = overlap_allowed(c, s, known) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B,
-                                      cudaStream_t s) {
+                                      cudaStream_t s, int known = OVL_PROBE) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;  // bulk copies need 16-byte alignment
     const bool tma = c->occ_tma > 0 && aligned && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
     if (SET == SET_P_III && c->split_ok && aligned && (c->variant == 3 || c->variant == 0)) {
-        cudaError_t e = launch_pdl(c, k_polymul_split<0>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B)),
+        cudaError_t e = launch_pdl(c, known, k_polymul_split<0>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B)),
                                    SplitShape::WARPS * 32, SplitShape::SMEM, s, x, y, z, B, c->d_tab_split);
         if (e != cudaSuccess) return (int)e;
     } else if (tma) {
-        cudaError_t e = launch_pdl(c, k_polymul_tma<SET>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, tiles)),
+        cudaError_t e = launch_pdl(c, known, k_polymul_tma<SET>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, tiles)),
                                    TmaCfg<SET>::WARPS * 32, c->smem_tma, s, x, y, z, B, c->d_tab[1]);
         if (e != cudaSuccess) return (int)e;
     }
@@ -246,15 +259,15 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
     if ((((uintptr_t)ahat | (uintptr_t)y) & 15) != 0) return QT_ERR_BAD_ARG;  // 128-bit / bulk-copy alignment
     if (SET == SET_P_III && c->split_ok && c->variant != 2) {
         const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B));
-        const cudaError_t e = bcast ? launch_pdl(c, k_polymul_split<1>, g, SplitShape::WARPS * 32, SplitShape::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab_split)
-                                    : launch_pdl(c, k_polymul_split<2>, g, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, ahat, y, z, B, c->d_tab_split);
+        const cudaError_t e = bcast ? launch_pdl(c, OVL_PROBE, k_polymul_split<1>, g, SplitShape::WARPS * 32, SplitShape::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab_split)
+                                    : launch_pdl(c, OVL_PROBE, k_polymul_split<2>, g, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, ahat, y, z, B, c->d_tab_split);
         if (e != cudaSuccess) return (int)e;
         c->launches++;
         return (int)cudaGetLastError();
     }
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
-    const cudaError_t e = bcast ? launch_pdl(c, k_polymul_ntt<SET, true>, grid, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab[1])
-                                : launch_pdl(c, k_polymul_ntt<SET, false>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, ahat, y, z, B, c->d_tab[1]);
+    const cudaError_t e = bcast ? launch_pdl(c, OVL_PROBE, k_polymul_ntt<SET, true>, grid, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab[1])
+                                : launch_pdl(c, OVL_PROBE, k_polymul_ntt<SET, false>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, ahat, y, z, B, c->d_tab[1]);
     if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
@@ -262,14 +275,14 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
 template <int SET, bool INV> int launch_ntt_tma(qt_ctx* c, uint32_t* a, size_t B) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
-    const cudaError_t e = launch_pdl(c, k_ntt_tma<SET, INV>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, a, B, c->d_tab[0]);
+    const cudaError_t e = launch_pdl(c, OVL_PROBE, k_ntt_tma<SET, INV>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, a, B, c->d_tab[0]);
     if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <bool INV> int launch_ntt_split(qt_ctx* c, uint32_t* a, size_t B) {
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, B));
-    const cudaError_t e = launch_pdl(c, k_ntt_split<INV>, grid, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, a, B, c->d_tab_split);
+    const cudaError_t e = launch_pdl(c, OVL_PROBE, k_ntt_split<INV>, grid, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, a, B, c->d_tab_split);
     if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
@@ -303,6 +316,12 @@ template <int SET> int launch_natural(qt_ctx* c, uint32_t* a, size_t B, bool inv
 }
 template <int SET> int launch_pointwise(qt_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t B) {
     const size_t words = B * Cfg<SET>::N;
+    if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)o) & 15) != 0) {  // 128-bit accesses need 16-byte alignment
+        const int g1 = (int)std::min<size_t>((size_t)c->num_sms * 8, (words + 255) / 256);
+        k_pointwise_scalar<SET><<<std::max(1, g1), 256, 0, c->stream>>>(a, b, o, words);
+        c->launches++;
+        return (int)cudaGetLastError();
+    }
     const int grid = (int)std::min<size_t>((size_t)c->num_sms * 8, (words / 4 + 255) / 256);
     k_pointwise<SET><<<std::max(1, grid), 256, 0, c->stream>>>(a, b, o, words);
     c->launches++;
@@ -470,7 +489,9 @@ int qt_create(int set, int device, qt_ctx** out) {
     if (!g.ok) return QT_ERR_NO_DEVICE;
     cudaDeviceProp prop;
     QT_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return QT_ERR_UNSUPPORTED;  // sm_100a cubin only
+    // the library carries ONE cubin, for sm_100a: it loads on compute capability 10.0 and nowhere else
+    // (sm_103 / sm_12x parts would fail later with "no kernel image")
+    if (prop.major != 10 || prop.minor != 0) return QT_ERR_UNSUPPORTED;
     qt_ctx* c = new (std::nothrow) qt_ctx();
     if (!c) return QT_ERR_NOMEM;
     c->set = set; c->device = device; c->p = p; c->num_sms = prop.multiProcessorCount;
@@ -483,7 +504,7 @@ int qt_create(int set, int device, qt_ctx** out) {
 
 int qt_destroy(qt_ctx* c) {
     if (!c) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     release_pipe(c);
     release_stage(c);
     for (int k = 0; k < 2; k++)
@@ -523,20 +544,20 @@ int qt_set_nussbaumer_variant(qt_ctx* c, int variant) {
 
 int qt_synchronize(qt_ctx* c) {
     if (!c) return QT_ERR_BAD_ARG;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     QT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 int qt_device_malloc(qt_ctx* c, size_t bytes, void** out) {
     if (!c || !out) return QT_ERR_BAD_ARG;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     QT_CUDA(cudaMalloc(out, bytes));
     return 0;
 }
 int qt_device_free(qt_ctx* c, void* d) {
     if (!c) return QT_ERR_BAD_ARG;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     QT_CUDA(cudaFree(d));
     return 0;
 }
@@ -551,13 +572,13 @@ int qt_host_free(void* h) {
 }
 int qt_memcpy_h2d(qt_ctx* c, void* d, const void* h, size_t bytes) {
     if (!c) return QT_ERR_BAD_ARG;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     QT_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 int qt_memcpy_d2h(qt_ctx* c, void* h, const void* d, size_t bytes) {
     if (!c) return QT_ERR_BAD_ARG;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     QT_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
     return 0;
 }
@@ -565,55 +586,55 @@ int qt_memcpy_d2h(qt_ctx* c, void* h, const void* d, size_t bytes) {
 int qt_ntt_forward(qt_ctx* c, uint32_t* a, size_t B) {
     if (!c || (!a && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_forward, c, a, B);
 }
 int qt_ntt_inverse(qt_ctx* c, uint32_t* a, size_t B) {
     if (!c || (!a && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_inverse, c, a, B);
 }
 int qt_ntt_forward_natural(qt_ctx* c, uint32_t* a, size_t B) {
     if (!c || (!a && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_natural, c, a, B, false);
 }
 int qt_ntt_inverse_natural(qt_ctx* c, uint32_t* a, size_t B) {
     if (!c || (!a && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_natural, c, a, B, true);
 }
 int qt_pointwise(qt_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t B) {
     if (!c || ((!a || !b || !o) && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_pointwise, c, a, b, o, B);
 }
 int qt_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B) {
     if (!c || ((!x || !y || !z) && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_polymul, c, x, y, z, B, c->stream);
 }
 int qt_polymul_ntt(qt_ctx* c, const uint32_t* ahat, int broadcast, const uint32_t* y, uint32_t* z, size_t B) {
     if (!c || ((!ahat || !y || !z) && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_polymul_ntt, c, ahat, broadcast != 0, y, z, B);
 }
 int qt_bitrev_copy(qt_ctx* c, const uint32_t* in, uint32_t* out, size_t B) {
     if (!c || ((!in || !out) && B) || (in == out && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     return QT_DISPATCH(c, launch_bitrev, c, in, out, B);
 }
 int qt_nussbaumer(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ring) {
-    if (!c || ((!x || !y || !z) && B) || (ring != QT_RING_2P32M1 && ring != QT_RING_MODQ)) return QT_ERR_BAD_ARG;
+    if (!c || ((!x || !y || !z) && B) || (ring != QT_RING_2P32M1 && ring != QT_RING_MODQ && ring != QT_RING_2P32M1_LIFT_Q)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     int rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, x, y, z, B, ring, c->nuss_variant, c->stream);
     if (rc == 0) c->launches++;
     return rc;
@@ -621,7 +642,7 @@ int qt_nussbaumer(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, 
 int qt_fill_uniform(qt_ctx* c, uint32_t* a, size_t count, uint64_t seed, uint64_t first) {
     if (!c || (!a && count)) return QT_ERR_BAD_ARG;
     if (!count) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     const int grid = (int)std::min<size_t>((size_t)c->num_sms * 8, (count + 255) / 256);
     k_fill_uniform<<<std::max(1, grid), 256, 0, c->stream>>>(a, count, seed, first, c->p.q);
     c->launches++;
@@ -663,7 +684,7 @@ static int staged_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint
             if (py) memcpy(hy, y + off, bytes);
             if (!rc) rc = (int)cudaMemcpyAsync(dy, py ? hy : y + off, bytes, cudaMemcpyHostToDevice, s);
             if (!rc) {
-                if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
+                if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s, OVL_YES);
                 else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, c->nuss_variant, s); if (!rc) c->launches++; }
             }
             if (!rc) rc = (int)cudaMemcpyAsync(pz ? hx : z + off, dx, bytes, cudaMemcpyDeviceToHost, s);
@@ -686,7 +707,7 @@ static int staged_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint
 static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int nuss_ring) {
     if (!c || ((!x || !y || !z) && B)) return QT_ERR_BAD_ARG;
     if (!B) return 0;
-    DeviceGuard g(c->device);
+    QT_GUARD(c->device);
     const bool px = is_pageable(x), py = is_pageable(y), pz = is_pageable(z);
     if (px || py || pz) return staged_pipeline(c, x, y, z, B, nuss_ring, px, py, pz);
     int rc = ensure_pipe(c);
@@ -706,7 +727,7 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
         rc = (int)cudaMemcpyAsync(dx, x + done * n, bytes, cudaMemcpyHostToDevice, s);
         if (!rc) rc = (int)cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s);
         if (!rc) {
-            if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s);
+            if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s, OVL_YES);
             else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, c->nuss_variant, s); if (!rc) c->launches++; }
         }
         if (!rc) rc = (int)cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s);
@@ -725,53 +746,198 @@ int qt_polymul_host(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z
     return host_pipeline(c, x, y, z, B, -1);
 }
 int qt_nussbaumer_host(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ring) {
-    if (ring != QT_RING_2P32M1 && ring != QT_RING_MODQ) return QT_ERR_BAD_ARG;
+    if (ring != QT_RING_2P32M1 && ring != QT_RING_MODQ && ring != QT_RING_2P32M1_LIFT_Q) return QT_ERR_BAD_ARG;
     return host_pipeline(c, x, y, z, B, ring);
 }
 
-// contexts of the one-shot multi-GPU form are created once per (set, device) and reused
-static std::mutex g_multi_mutex;
-static qt_ctx* g_multi_ctx[NUM_SETS][64];
+// ---- in-process multi-GPU: contiguous slices [g*B/G, (g+1)*B/G), no collective -------------------
+// A qt_multi owns one context and one persistent host thread per device.  Each thread binds itself next to its GPU
+// (qt_bind_thread_to_device) BEFORE it creates the context, so the pinned staging buffers of the pageable path are
+// allocated and first touched on that NUMA node, then sleeps until a job arrives.  No process-global state: two
+// callers use two handles.  Like a context, one handle is not thread-safe.
+struct qt_multi {
+    int set = -1, ngpus = 0;
+    RtParams p{};
+    std::vector<qt_ctx*> ctx;
+    std::vector<std::thread> th;
+    std::vector<int> rc;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    uint64_t job_id = 0;
+    int pending = 0;
+    bool quit = false;
+    const uint32_t *x = nullptr, *y = nullptr;
+    uint32_t* z = nullptr;
+    size_t B = 0;
+};
 
-int qt_polymul_host_multi(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ngpus) {
+static void multi_worker(qt_multi* mh, int g) {
+    int cpus = 0;
+    (void)qt_bind_thread_to_device(g, &cpus);
+    int rc = qt_create(mh->set, g, &mh->ctx[g]);
+    if (!rc) mh->ctx[g]->stage_share = mh->ngpus;  // the devices share the host cores of the staged (pageable) path
+    uint64_t seen = 0;
+    {
+        std::lock_guard<std::mutex> lk(mh->m);
+        mh->rc[g] = rc;
+        if (--mh->pending == 0) mh->cv_done.notify_all();
+    }
+    for (;;) {
+        std::unique_lock<std::mutex> lk(mh->m);
+        mh->cv_job.wait(lk, [&] { return mh->quit || mh->job_id != seen; });
+        if (mh->quit) break;
+        seen = mh->job_id;
+        const size_t lo = mh->B * (size_t)g / mh->ngpus, hi = mh->B * (size_t)(g + 1) / mh->ngpus, n = mh->p.n;
+        const uint32_t *x = mh->x, *y = mh->y;
+        uint32_t* z = mh->z;
+        lk.unlock();
+        int r = mh->ctx[g] ? 0 : QT_ERR_NO_DEVICE;
+        if (!r && hi > lo) r = qt_polymul_host(mh->ctx[g], x + lo * n, y + lo * n, z + lo * n, hi - lo);
+        lk.lock();
+        mh->rc[g] = r;
+        if (--mh->pending == 0) mh->cv_done.notify_all();
+    }
+    if (mh->ctx[g]) { qt_destroy(mh->ctx[g]); mh->ctx[g] = nullptr; }
+}
+
+int qt_multi_create(int set, int ngpus, qt_multi** out) {
     RtParams p;
+    if (!out) return QT_ERR_BAD_ARG;
+    *out = nullptr;
     if (!rt_params(set, &p)) return QT_ERR_BAD_SET;
-    if ((!x || !y || !z) && B) return QT_ERR_BAD_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return QT_ERR_NO_DEVICE;
-    ndev = std::min(ndev, 64);
     if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
-    if (!B) return 0;
-    std::lock_guard<std::mutex> lk(g_multi_mutex);  // contexts are not thread-safe
-    // contiguous slices [g*B/G, (g+1)*B/G), one host thread per device, no collective
-    std::vector<int> rcs(ngpus, 0);
-    std::vector<std::thread> th;
-    for (int gidx = 0; gidx < ngpus; gidx++) {
-        th.emplace_back([&, gidx]() {
-            const size_t lo = B * gidx / ngpus, hi = B * (gidx + 1) / ngpus;
-            if (hi == lo) return;
-            int rc = 0;
-            if (!g_multi_ctx[set][gidx]) rc = qt_create(set, gidx, &g_multi_ctx[set][gidx]);
-            if (!rc && g_multi_ctx[set][gidx]->stage_share != ngpus) {  // the devices share the host cores
-                DeviceGuard dg(gidx);
-                release_stage(g_multi_ctx[set][gidx]);
-                g_multi_ctx[set][gidx]->stage_share = ngpus;
-            }
-            if (!rc) rc = qt_polymul_host(g_multi_ctx[set][gidx], x + lo * p.n, y + lo * p.n, z + lo * p.n, hi - lo);
-            rcs[gidx] = rc;
-        });
+    qt_multi* mh = new (std::nothrow) qt_multi();
+    if (!mh) return QT_ERR_NOMEM;
+    mh->set = set; mh->ngpus = ngpus; mh->p = p;
+    mh->ctx.assign(ngpus, nullptr);
+    mh->rc.assign(ngpus, 0);
+    mh->pending = ngpus;
+    for (int g = 0; g < ngpus; g++) mh->th.emplace_back(multi_worker, mh, g);
+    {
+        std::unique_lock<std::mutex> lk(mh->m);
+        mh->cv_done.wait(lk, [&] { return mh->pending == 0; });
     }
-    for (auto& t : th) t.join();
-    for (int rc : rcs)
+    for (int g = 0; g < ngpus; g++)
+        if (mh->rc[g]) {
+            const int rc = mh->rc[g];
+            qt_multi_destroy(mh);
+            return rc;
+        }
+    *out = mh;
+    return 0;
+}
+
+int qt_multi_destroy(qt_multi* mh) {
+    if (!mh) return 0;
+    {
+        std::lock_guard<std::mutex> lk(mh->m);
+        mh->quit = true;
+    }
+    mh->cv_job.notify_all();
+    for (auto& t : mh->th) t.join();
+    delete mh;
+    return 0;
+}
+
+int qt_multi_gpus(qt_multi* mh, int* out) {
+    if (!mh || !out) return QT_ERR_BAD_ARG;
+    *out = mh->ngpus;
+    return 0;
+}
+
+int qt_multi_polymul_host(qt_multi* mh, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B) {
+    if (!mh || ((!x || !y || !z) && B)) return QT_ERR_BAD_ARG;
+    if (!B) return 0;
+    std::unique_lock<std::mutex> lk(mh->m);
+    mh->x = x; mh->y = y; mh->z = z; mh->B = B;
+    mh->pending = mh->ngpus;
+    mh->job_id++;
+    mh->cv_job.notify_all();
+    mh->cv_done.wait(lk, [&] { return mh->pending == 0; });
+    for (int rc : mh->rc)
         if (rc) return rc;
     return 0;
 }
 
-int qt_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_multi_mutex);
-    for (int s = 0; s < NUM_SETS; s++)
-        for (int d = 0; d < 64; d++)
-            if (g_multi_ctx[s][d]) { qt_destroy(g_multi_ctx[s][d]); g_multi_ctx[s][d] = nullptr; }
+// one-shot form: a handle for the duration of the call (contexts, streams and staging buffers are set up and torn
+// down every time — callers that multiply more than once keep a qt_multi)
+int qt_polymul_host_multi(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int ngpus) {
+    RtParams p;
+    if (!rt_params(set, &p)) return QT_ERR_BAD_SET;
+    if ((!x || !y || !z) && B) return QT_ERR_BAD_ARG;
+    qt_multi* mh = nullptr;
+    int rc = qt_multi_create(set, ngpus, &mh);
+    if (rc) return rc;
+    rc = qt_multi_polymul_host(mh, x, y, z, B);
+    qt_multi_destroy(mh);
+    return rc;
+}
+
+int qt_shutdown(void) { return 0; }  // kept for ABI compatibility: the library holds no process-global contexts any more
+
+// ---- CUDA graphs for launch-bound batches -------------------------------------------------------------------------
+// A caller with a fixed sequence of small launches (B <= 4096: the kernels take a few microseconds, the host-side
+// launch path costs as much) records the sequence once and replays it: between qt_graph_begin and qt_graph_end every
+// device-pointer entry point of this context is CAPTURED on the ctx stream instead of executed.  Programmatic dependent
+// launches are kept: inside the graph they become programmatic edges, so the prologue of node k+1 still overlaps
+// the tail of node k.
+struct qt_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int device = -1;
+    uint64_t kernels = 0;
+};
+
+int qt_graph_begin(qt_ctx* c) {
+    if (!c || c->capturing) return QT_ERR_BAD_ARG;
+    QT_GUARD(c->device);
+    (void)overlap_allowed(c, c->stream, OVL_PROBE);  // stream-flag query now, not inside the capture
+    QT_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = true;
+    c->capture_launches0 = c->launches;
+    return 0;
+}
+
+int qt_graph_end(qt_ctx* c, qt_graph** out) {
+    if (!c || !out || !c->capturing) return QT_ERR_BAD_ARG;
+    *out = nullptr;
+    QT_GUARD(c->device);
+    c->capturing = false;
+    const uint64_t recorded = c->launches - c->capture_launches0;
+    c->launches = c->capture_launches0;  // recorded, not run
+    cudaGraph_t g = nullptr;
+    QT_CUDA(cudaStreamEndCapture(c->stream, &g));
+    qt_graph* h = new (std::nothrow) qt_graph();
+    if (!h) { cudaGraphDestroy(g); return QT_ERR_NOMEM; }
+    h->graph = g; h->device = c->device; h->kernels = recorded;
+    const cudaError_t e = cudaGraphInstantiate(&h->exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); delete h; return (int)e; }
+    *out = h;
+    return 0;
+}
+
+int qt_graph_launch(qt_ctx* c, qt_graph* g) {
+    if (!c || !g || !g->exec || c->capturing || g->device != c->device) return QT_ERR_BAD_ARG;
+    QT_GUARD(c->device);
+    QT_CUDA(cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->kernels;
+    return 0;
+}
+
+int qt_graph_destroy(qt_graph* g) {
+    if (!g) return 0;
+    DeviceGuard dg(g->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return 0;
+}
+
+int qt_graph_kernel_count(qt_graph* g, uint64_t* out) {
+    if (!g || !out) return QT_ERR_BAD_ARG;
+    *out = g->kernels;
     return 0;
 }
 

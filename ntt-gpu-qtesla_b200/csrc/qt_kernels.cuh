@@ -814,6 +814,16 @@ k_pointwise(const uint32_t* a, const uint32_t* b, uint32_t* c, size_t words) {
     }
 }
 
+// same for operands that are only 4-byte aligned (a view into a larger array): one word per thread, still coalesced
+template <int SET>
+__global__ void __launch_bounds__(256)
+k_pointwise_scalar(const uint32_t* a, const uint32_t* b, uint32_t* c, size_t words) {
+    using T = Tile<SET>;
+    const TwPair r2{T::C::R_MODQ, (uint32_t)(((uint64_t)T::C::R_MODQ << 32) / T::Q)};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
+        c[i] = T::csub(T::mul_shoup(T::mul_mont(a[i], b[i]), r2), T::Q);
+}
+
 // out[b*n + j] = in[b*n + brv(j)]   (bit_reverse_copy_tbl_gpu, NTT.cu:487-492)
 // One warp per polynomial.  Lane L reads the coefficients L + 32 r (one 128-byte line per warp
 // instruction); their bit-reversed positions brv(L + 32 r) = R*brv5(L) + brv_logR(r), R = n/32, form ONE

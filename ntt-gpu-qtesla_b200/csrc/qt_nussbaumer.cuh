@@ -99,6 +99,22 @@ template <int SET> struct NussOps<SET, 0> {  // Z/(2^32-1), NTT.cu:102-134
 #endif
     }
     static QT_HD uint32_t fold(uint64_t t) { return add((uint32_t)t, (uint32_t)(t >> 32)); }
+    // ---- QT_RING_2P32M1_LIFT_Q: Z_q operands through the ring 2^32-1 -------------------------
+    // A canonical residue v in [0, q) enters as its CENTRED integer representative v~ in (-q/2, q/2] (negative
+    // values as 2^32-1 + v~); the ring product is the INTEGER negacyclic product as long as every integer
+    // coefficient satisfies |c| < 2^31 (sum over i of |x~_i| |y~_(k-i)| < 2^31 is sufficient: e.g. qTESLA's s*c, e*c with a
+    // small secret and a weight-h ternary challenge, or uniform * ternary for the 23-bit moduli); the signed lift of
+    // the ring value reduced mod q is then the Z_q product.  Outside the precondition the result is NOT the Z_q product.
+    static constexpr uint32_t Q = Cfg<SET>::Q;
+    static QT_HD uint32_t lift_in(uint32_t v) { return v > Q / 2 ? v + (0xFFFFFFFFu - Q) : v; }
+    static QT_HD uint32_t lift_out(uint32_t r) {
+        r = norm(r);
+        const bool negative = r >= 0x80000000u;
+        const uint32_t mag = negative ? 0xFFFFFFFFu - r : r;                       // |signed lift| < 2^31
+        uint32_t m = mag - mulhi32(mag, Cfg<SET>::MU32) * Q;                       // [0, 2q)
+        m = umin32(m, m - Q);                                                      // [0, q)
+        return (negative && m != 0) ? Q - m : m;
+    }
 };
 
 template <int SET> struct NussOps<SET, 1> {  // Z_q, operands canonical
@@ -337,10 +353,11 @@ template <int SET, int RING> struct Nuss {
 
     // phase 0: global -> rows (both copies).  tid strides over the n coefficients of polynomial p.
     static QT_HD void load(uint32_t tid, uint32_t nthreads, const uint32_t* gx, const uint32_t* gy,
-                           uint32_t* sx, uint32_t* sy) {
+                           uint32_t* sx, uint32_t* sy, bool lift = false) {
         for (uint32_t g = tid; g < K::N; g += nthreads) {
             const uint32_t i = g % M, j = g / M;
-            const uint32_t vx = gx[g], vy = gy[g];
+            uint32_t vx = gx[g], vy = gy[g];
+            if (RING == 0 && lift) { vx = NussOps<SET, 0>::lift_in(vx); vy = NussOps<SET, 0>::lift_in(vy); }
             sx[i * K::XS + j] = vx; sx[(i + M) * K::XS + j] = vx;
             sy[i * K::YS + j] = vy; sy[(i + M) * K::YS + j] = vy;
         }
@@ -470,12 +487,13 @@ template <int SET, int RING> struct Nuss {
     }
 
     // final phase: recombination and coalesced store (NTT.cu:271-276)
-    static QT_HD void store(uint32_t tid, uint32_t nthreads, const uint32_t* z, uint32_t* gz) {
+    static QT_HD void store(uint32_t tid, uint32_t nthreads, const uint32_t* z, uint32_t* gz, bool lift = false) {
         for (uint32_t g = tid; g < K::N; g += nthreads) {
             const uint32_t i = g % M, j = g / M;
             uint32_t v;
             if (j == 0) v = O::sub(z[i * K::XS], z[(M + i) * K::XS + R - 1]);
             else v = O::add(z[i * K::XS + j], z[(M + i) * K::XS + j - 1]);
+            if (RING == 0 && lift) v = NussOps<SET, 0>::lift_out(v);
             gz[g] = v;
         }
     }
@@ -485,7 +503,7 @@ template <int SET, int RING> struct Nuss {
 
 template <int SET, int RING, bool REC = false>
 __global__ void __launch_bounds__(NussCfg<SET>::THREADS)
-k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, uint32_t lift) {
     static_assert(!REC || RING == 1, "recursive row products exist for Z_q only");
     using K = NussCfg<SET>;
     using NU = Nuss<SET, RING>;
@@ -502,7 +520,7 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
             const uint32_t per = K::THREADS / K::P, p = tid / per;
             if (p < np)
                 NU::load(tid % per, per, x + (p0 + p) * K::N, y + (p0 + p) * K::N, smem + p * K::POLY_WORDS,
-                         smem + p * K::POLY_WORDS + K::X_WORDS);
+                         smem + p * K::POLY_WORDS + K::X_WORDS, lift != 0);
         }
         __syncthreads();
         // forward stages: P polys x 2 operands x m row butterflies per stage, one warp each
@@ -545,7 +563,7 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
         }
         {
             const uint32_t per = K::THREADS / K::P, p = tid / per;
-            if (p < np) NU::store(tid % per, per, smem + p * K::POLY_WORDS, z + (p0 + p) * K::N);
+            if (p < np) NU::store(tid % per, per, smem + p * K::POLY_WORDS, z + (p0 + p) * K::N, lift != 0);
         }
         __syncthreads();
     }
@@ -728,7 +746,7 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
 
 template <int SET, int RING, int MODE = 0>
 __global__ void __launch_bounds__(NussWarp<SET, RING, MODE>::WARPS * 32)
-k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, uint32_t lift) {
     using W = NussWarp<SET, RING, MODE>;
     using K = NussCfg<SET>;
     using O = typename W::O;
@@ -751,6 +769,10 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
             for (uint32_t c = 0; c < K::M / 4; c++) {
                 const uint4 u = g[c];
                 v[4 * c] = u.x; v[4 * c + 1] = u.y; v[4 * c + 2] = u.z; v[4 * c + 3] = u.w;
+            }
+            if (RING == 0 && lift) {  // QT_RING_2P32M1_LIFT_Q: centred representatives of the Z_q operands
+#pragma unroll
+                for (uint32_t i = 0; i < K::M; i++) v[i] = NussOps<SET, 0>::lift_in(v[i]);
             }
             if (W::CENTRE_X) {
                 const uint32_t thr = op ? 0xFFFFFFFFu : T::Q / 2;  // x only
@@ -791,6 +813,7 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
                 uint32_t r = (lane == 0) ? O::sub(v[i], up) : O::add(v[i], up);
                 if (W::LAZYQ) r = T::scanon(T::smul_shoup(r, TwPair{1u, T::C::MU32}));  // any |r| < 2^31 -> [0, q)
                 else if (RING == 1) r = T::csub(T::mul_shoup(r, rfix), T::Q);
+                else if (lift) r = NussOps<SET, 0>::lift_out(r);
                 o[k] = r;
             }
             gz[c] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -845,6 +868,8 @@ template <int SET>
 int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring, int variant,
                 cudaStream_t s) {
     using K = NussCfg<SET>;
+    const uint32_t lift = ring == 2 ? 1u : 0u;  // QT_RING_2P32M1_LIFT_Q: the ring 2^32-1 kernels with the lift epilogue
+    if (ring == 2) ring = 0;
     const bool f64 = ring == 1 && nuss_has_f64<SET>() && (variant == NUSS_FP64 || (variant == NUSS_AUTO && QT_NUSS_AUTO_F64));
     const bool rec = ring == 1 && !f64 && (variant == NUSS_RECURSIVE || (variant == NUSS_AUTO && QT_NUSS_AUTO_RECURSIVE));
     if (variant == NUSS_FP64 && ring == 1 && !nuss_has_f64<SET>()) return -4;  // QT_ERR_UNSUPPORTED
@@ -852,19 +877,19 @@ int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z,
         if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15) != 0) return -2;  // 128-bit accesses
         using W = NussWarp<SET, 0>;
         const int g = (int)(batch < (size_t)max_grid ? batch : (size_t)max_grid);  // small batches spread over all SMs
-        if (ring == 0) k_nussbaumer_warp<SET, 0, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        if (ring == 0) k_nussbaumer_warp<SET, 0, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch, lift);
         else if (f64) {
             if constexpr (nuss_has_f64<SET>())
-                k_nussbaumer_warp<SET, 1, 2><<<g, NussWarp<SET, 1, 2>::WARPS * 32, NussWarp<SET, 1, 2>::SMEM_BYTES, s>>>(x, y, z, batch);
-        } else if (rec) k_nussbaumer_warp<SET, 1, 1><<<g, NussWarp<SET, 1, 1>::WARPS * 32, NussWarp<SET, 1, 1>::SMEM_BYTES, s>>>(x, y, z, batch);
-        else k_nussbaumer_warp<SET, 1, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+                k_nussbaumer_warp<SET, 1, 2><<<g, NussWarp<SET, 1, 2>::WARPS * 32, NussWarp<SET, 1, 2>::SMEM_BYTES, s>>>(x, y, z, batch, lift);
+        } else if (rec) k_nussbaumer_warp<SET, 1, 1><<<g, NussWarp<SET, 1, 1>::WARPS * 32, NussWarp<SET, 1, 1>::SMEM_BYTES, s>>>(x, y, z, batch, lift);
+        else k_nussbaumer_warp<SET, 1, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch, lift);
         return (int)cudaGetLastError();
     } else {
         const size_t groups = (batch + K::P - 1) / K::P;
         const int grid = (int)(groups < (size_t)max_grid ? groups : (size_t)max_grid);
-        if (ring == 0) k_nussbaumer<SET, 0, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
-        else if (rec) k_nussbaumer<SET, 1, true><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
-        else k_nussbaumer<SET, 1, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+        if (ring == 0) k_nussbaumer<SET, 0, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch, lift);
+        else if (rec) k_nussbaumer<SET, 1, true><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch, lift);
+        else k_nussbaumer<SET, 1, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch, lift);
         return (int)cudaGetLastError();
     }
 }

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("QT_LIB_PATH") or os.path.join(PKG_DIR, "libqtesla_b20
 SET_I, SET_III, SET_P_I, SET_P_III = 0, 1, 2, 3
 SET_NAMES = {SET_I: "qTESLA-I", SET_III: "qTESLA-III", SET_P_I: "qTESLA-p-I", SET_P_III: "qTESLA-p-III"}
 TABLE_BITREV, TABLE_PHI, TABLE_INVPHI, TABLE_TF0, TABLE_TI0 = range(5)
-RING_2P32M1, RING_MODQ = 0, 1
+RING_2P32M1, RING_MODQ, RING_2P32M1_LIFT_Q = 0, 1, 2
 
 _vp = C.c_void_p
 _sz = C.c_size_t
@@ -62,8 +62,20 @@ _SIGNATURES = {
     "qt_polymul_host_multi": (C.c_int, [C.c_int, _vp, _vp, _vp, _sz, C.c_int]),
     "qt_nussbaumer_host": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.c_int]),
     "qt_shutdown": (C.c_int, []),
+    "qt_graph_begin": (C.c_int, [_vp]),
+    "qt_graph_end": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "qt_graph_launch": (C.c_int, [_vp, _vp]),
+    "qt_graph_destroy": (C.c_int, [_vp]),
+    "qt_graph_kernel_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "qt_multi_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),
+    "qt_multi_destroy": (C.c_int, [_vp]),
+    "qt_multi_gpus": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "qt_multi_polymul_host": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
     "qt_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "qt_kernel_info": (C.c_int, [_vp] + [C.POINTER(C.c_int)] * 5),
+    "qt_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, _sz]),
+    "qt_device_numa_node": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "qt_bind_thread_to_device": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
 }
 
 _lib = None
@@ -134,6 +146,39 @@ def polymul_host_multi(param_set, x, y, ngpus=0):
     return z
 
 
+class MultiEngine:
+    """qt_multi: one context + one NUMA-bound host thread per GPU, the batch sharded contiguously (no collective)."""
+
+    def __init__(self, param_set=SET_III, ngpus=0):
+        self._h = _vp()
+        self.params = get_params(param_set)
+        self.n, self.q = self.params.n, self.params.q
+        _check(lib().qt_multi_create(param_set, ngpus, C.byref(self._h)))
+        k = C.c_int(0)
+        _check(lib().qt_multi_gpus(self._h, C.byref(k)))
+        self.ngpus = k.value
+
+    def polymul_host(self, x, y, z=None, batch=None):
+        if z is None:
+            z = np.empty_like(x)
+        if batch is None:
+            assert x.size % self.n == 0
+            batch = x.size // self.n
+        _check(lib().qt_multi_polymul_host(self._h, _addr(x), _addr(y), _addr(z), batch))
+        return z
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().qt_multi_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """One context = one GPU + one parameter set (qt_create).  Not thread-safe."""
 
@@ -198,6 +243,26 @@ class Engine:
         sz = a.size if isinstance(a, np.ndarray) else a.numel()
         assert sz % self.n == 0, "array must hold whole polynomials"
         return sz // self.n
+
+    # -- CUDA graphs: record a fixed launch sequence once, replay it with one host call (launch-bound batches)
+    def graph_begin(self):
+        _check(lib().qt_graph_begin(self._h))
+
+    def graph_end(self):
+        g = _vp()
+        _check(lib().qt_graph_end(self._h, C.byref(g)))
+        return g
+
+    def graph_launch(self, g):
+        _check(lib().qt_graph_launch(self._h, g))
+
+    def graph_destroy(self, g):
+        _check(lib().qt_graph_destroy(g))
+
+    def graph_kernel_count(self, g):
+        v = C.c_uint64(0)
+        _check(lib().qt_graph_kernel_count(g, C.byref(v)))
+        return v.value
 
     # -- device-pointer operators (asynchronous on the context stream)
     def ntt_forward(self, d_a, batch=None):

@@ -115,6 +115,11 @@ uint64_t qto_splitmix64(uint64_t x);
 int qto_polymul_omp(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B,
                     int threads);
 int qto_max_threads(void);
+/* qTESLA-style CPU path (qt_cpu_fast.c: Montgomery reduce with PARAM_QINV, merged twiddles, lazy ranges;
+ * "restatement, qTESLA source unavailable"), OpenMP over polynomials; returns threads used.  Results are
+ * canonical and equal to qto_polymul / qto_ntt_forward. */
+int qto_fast_polymul(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int threads);
+void qto_fast_ntt_forward(int set, uint32_t* a, size_t B);
 
 #ifdef __cplusplus
 }

@@ -137,4 +137,77 @@ int qtref_max_threads(void) {
 #endif
 }
 
+/* ---- the reference's own GPU kernels as a same-box baseline --------------------------------
+ * Launches the UNMODIFIED __global__ kernels of NTT.cu in the order of test_NTT_CT_GS_nega_gpu
+ * (NTT.cu:2388-2425: bit_reverse_copy_tbl_Phi_gpu x2, 10 radix2NTT_gpu0/1 levels per operand, pointwise_mult,
+ * 10 GS_radix2INTT_gpu0/2 levels, bit_reverse_copy_tbl_invPhi_gpu = 34 launches), with the grid taken from the
+ * caller's batch instead of the BATCH macro (the kernels index by blockIdx.x, NTT.cu:957).  Of the five drivers
+ * this is the one whose forward path applies the psi scale, i.e. computes the negacyclic product.
+ * x, y, z are HOST arrays of B*1024 words.  Times with CUDA events:
+ *   *kernel_ms = the 34 launches, operands device-resident (per repetition, averaged over reps)
+ *   *total_ms  = synchronous cudaMemcpy of x, y + the launches + cudaMemcpy of z, the reference's own
+ *                convention (NTT.cu:2383-2428), with the caller's buffers as they are (pinned or pageable)
+ * Returns 0, or a cudaError_t. */
+static void ref_ct_gs_launches(uint32_t* d_x, uint32_t* d_X, uint32_t* d_y, uint32_t* d_Y, uint32_t* d_Z, unsigned B) {
+    uint32_t* unused = nullptr; /* the reference passes uninitialised d_tf0/d_ti0; its kernels read __constant__ tables */
+    bit_reverse_copy_tbl_Phi_gpu<<<B, NTTSIZE>>>(d_x, d_X);
+    bit_reverse_copy_tbl_Phi_gpu<<<B, NTTSIZE>>>(d_y, d_Y);
+    for (int op = 0; op < 2; op++) {
+        uint32_t* d = op ? d_Y : d_X;
+        for (unsigned lvl = 1; lvl <= 5; lvl++) radix2NTT_gpu0<<<B, NTTSIZE >> lvl>>>(d, unused, 1u << lvl, lvl);
+        for (unsigned lvl = 6; lvl <= 10; lvl++) radix2NTT_gpu1<<<B, 1u << (lvl - 1)>>>(d, unused, 1u << (lvl - 1), lvl);
+    }
+    pointwise_mult<<<B, NTTSIZE>>>(d_X, d_Y, d_Z);
+    for (unsigned lvl = 0; lvl <= 4; lvl++) GS_radix2INTT_gpu0<<<B, 512u >> lvl>>>(d_Z, unused, lvl);
+    for (unsigned lvl = 5; lvl <= 9; lvl++) GS_radix2INTT_gpu2<<<B, 32u << (lvl - 5)>>>(d_Z, unused, lvl);
+    bit_reverse_copy_tbl_invPhi_gpu<<<B, NTTSIZE>>>(d_Z, d_x);
+}
+
+int qtref_gpu_ct_gs(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B, int reps, float* kernel_ms, float* total_ms) {
+    const size_t bytes = B * NTTSIZE * sizeof(uint32_t);
+    uint32_t* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaMalloc((void**)&d[i], bytes);
+    cudaEvent_t e0, e1;
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+        /* reference convention: copies inside the timed region */
+        float acc = 0.f;
+        for (int r = 0; r < reps + 1 && e == cudaSuccess; r++) { /* first pass = warm-up */
+            cudaEventRecord(e0);
+            cudaMemcpy(d[0], x, bytes, cudaMemcpyHostToDevice);
+            cudaMemcpy(d[2], y, bytes, cudaMemcpyHostToDevice);
+            ref_ct_gs_launches(d[0], d[1], d[2], d[3], d[4], (unsigned)B);
+            cudaMemcpy(z, d[0], bytes, cudaMemcpyDeviceToHost);
+            cudaEventRecord(e1);
+            e = cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r) acc += ms;
+        }
+        if (total_ms) *total_ms = acc / reps;
+        /* kernel-only: operands resident (d_x is overwritten by the result, so it is refreshed outside the timer) */
+        acc = 0.f;
+        for (int r = 0; r < reps && e == cudaSuccess; r++) {
+            cudaMemcpy(d[0], x, bytes, cudaMemcpyHostToDevice);
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0);
+            ref_ct_gs_launches(d[0], d[1], d[2], d[3], d[4], (unsigned)B);
+            cudaEventRecord(e1);
+            e = cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            acc += ms;
+        }
+        if (kernel_ms) *kernel_ms = acc / reps;
+        if (e == cudaSuccess) e = cudaGetLastError();
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    for (int i = 0; i < 5; i++)
+        if (d[i]) cudaFree(d[i]);
+    return (int)e;
+}
+
 } /* extern "C" */

@@ -67,6 +67,9 @@ class Oracle:
         L.qto_fill_splitmix.restype = None
         L.qto_bitrev.argtypes = [C.c_uint32, C.c_uint32]
         L.qto_bitrev.restype = C.c_uint32
+        L.qto_fast_polymul.argtypes = [C.c_int, _u32p, _u32p, _u32p, C.c_size_t, C.c_int]
+        L.qto_fast_ntt_forward.argtypes = [C.c_int, _u32p, C.c_size_t]
+        L.qto_fast_ntt_forward.restype = None
 
     def params(self, s):
         p = Params()
@@ -129,6 +132,20 @@ class Oracle:
             assert self.lib.qto_polymul_omp(s, _p(x), _p(y), _p(z), self._B(s, x), threads) > 0
         return z
 
+    def fast_polymul(self, s, x, y, threads=1):
+        """qTESLA-style CPU path (oracle/qt_cpu_fast.c: Montgomery, merged twiddles, lazy ranges)"""
+        x = np.ascontiguousarray(x, np.uint32)
+        y = np.ascontiguousarray(y, np.uint32)
+        z = np.empty_like(x)
+        if x.size:
+            assert self.lib.qto_fast_polymul(s, _p(x), _p(y), _p(z), self._B(s, x), threads) > 0
+        return z
+
+    def fast_forward(self, s, a):
+        a = np.ascontiguousarray(a, np.uint32).copy()
+        self.lib.qto_fast_ntt_forward(s, _p(a), self._B(s, a))
+        return a
+
     def schoolbook(self, s, x, y):
         x = np.ascontiguousarray(x, np.uint32)
         y = np.ascontiguousarray(y, np.uint32)
@@ -188,6 +205,8 @@ class Reference:
         L.qtref_naive.argtypes = [_u32p, _u32p, _u32p, C.c_uint]
         L.qtref_barrett_cpu.argtypes = [C.c_ulonglong]
         L.qtref_barrett_cpu.restype = C.c_uint
+        if hasattr(L, "qtref_gpu_ct_gs"):
+            L.qtref_gpu_ct_gs.argtypes = [_u32p, _u32p, _u32p, C.c_size_t, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         self.n = L.qtref_n()
         self.q = L.qtref_q()
 
@@ -223,6 +242,17 @@ class Reference:
         z = np.empty_like(x)
         self.lib.qtref_nussbaumer(_p(x), _p(y), _p(z), x.size // self.n)
         return z
+
+    def gpu_ct_gs(self, x, y, reps=3):
+        """The reference's own GPU kernels (unmodified), launch order of test_NTT_CT_GS_nega_gpu (NTT.cu:2388-2425).
+        Returns (z, kernel_ms, total_ms): kernel-only and copy-inclusive time per batch."""
+        x = np.ascontiguousarray(x, np.uint32)
+        y = np.ascontiguousarray(y, np.uint32)
+        z = np.empty_like(x)
+        k, t = C.c_float(0), C.c_float(0)
+        rc = self.lib.qtref_gpu_ct_gs(_p(x), _p(y), _p(z), x.size // self.n, reps, C.byref(k), C.byref(t))
+        assert rc == 0, f"reference GPU kernels failed: cudaError {rc}"
+        return z, k.value, t.value
 
     def max_threads(self):
         return self.lib.qtref_max_threads()

@@ -78,3 +78,32 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dp, f)).read()
                 assert "oracle" not in text.lower().replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_multi_handle_and_placement_fail_loudly_without_device(qt):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(qt.QtError):
+        qt.MultiEngine(qt.SET_III, 0)
+    x = np.zeros(1024, np.uint32)
+    with pytest.raises(qt.QtError):
+        qt.polymul_host_multi(qt.SET_III, x, x, 0)
+    with pytest.raises(qt.QtError):
+        qt.numa.gpu_numa_node(0)
+
+
+def test_dropin_binary_is_the_reference_main_linked_against_the_library():
+    """`make -C oracle dropin` (needs /root/reference at build time): the reference's own main.cu with the
+    INTEGRATION.md patch, linked against libqtesla_b200.so — here it must resolve the library and, with no GPU,
+    fail with the library's error message instead of computing anything on the CPU."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "dropin_main")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_main not built")
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libqtesla_b200.so" in ldd and "not found" not in ldd
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "-speedgpu", "3"], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and "no usable CUDA device" in r.stderr

@@ -173,3 +173,40 @@ def test_splitmix_stream(oracle):
     assert np.array_equal(a[8:], b) and a.max() < 8404993
     # value pinned so that the device generator can be checked against it
     assert int(oracle.splitmix(0, 0, 2 ** 32 - 1, 1)[0]) == (0xE220A8397B1DCDAF % (2 ** 32 - 1))
+
+
+# ---- qTESLA-style Montgomery / merged-twiddle CPU baseline (oracle/qt_cpu_fast.c) ----------
+@pytest.mark.parametrize("s", ALL_SETS)
+def test_fast_cpu_path_equals_port_and_schoolbook(oracle, s):
+    """the restatement of the qTESLA C poly_ntt/poly_mul is pinned to the port (itself pinned to the reference)
+    and to the O(n^2) schoolbook; edge operands: all q-1, all 0, x = 1, x = X^(n-1) * y = X"""
+    p = oracle.params(s)
+    rng = np.random.default_rng(900 + s)
+    B = 12
+    x = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    y = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    x[: p.n] = p.q - 1
+    y[: p.n] = p.q - 1
+    x[p.n: 2 * p.n] = 0
+    x[2 * p.n: 3 * p.n] = 0
+    x[2 * p.n] = 1
+    x[3 * p.n: 4 * p.n] = 0
+    x[4 * p.n - 1] = 1
+    y[3 * p.n: 4 * p.n] = 0
+    y[3 * p.n + 1] = 1
+    z = oracle.fast_polymul(s, x, y, threads=2)
+    assert np.array_equal(z, oracle.polymul(s, x, y))
+    assert np.array_equal(z[: 4 * p.n], oracle.schoolbook(s, x[: 4 * p.n], y[: 4 * p.n]))
+    assert np.array_equal(z[2 * p.n: 3 * p.n], y[2 * p.n: 3 * p.n]) and z[3 * p.n] == p.q - 1
+    # NTT-domain layout: bit for bit the reference's Phi-scale + radix2NTTGS output
+    assert np.array_equal(oracle.fast_forward(s, x), oracle.forward(s, x))
+
+
+def test_fast_cpu_path_golden_and_reference(oracle, golden, reference):
+    d = np.load(os.path.join(HERE, "golden", "golden_III_b2.npz"))
+    assert np.array_equal(oracle.fast_polymul(SET_III, d["x"], d["y"]), d["z"])
+    assert sha(oracle.fast_forward(SET_III, d["x"])) == golden["III_random_b2"]["fwd_sha256"]
+    rng = np.random.default_rng(31)
+    x = rng.integers(0, 8404993, 64 * 1024, dtype=np.uint32)
+    y = rng.integers(0, 8404993, 64 * 1024, dtype=np.uint32)
+    assert np.array_equal(oracle.fast_polymul(SET_III, x, y, threads=2), reference.polymul(x, y, 0, 2))
