@@ -66,6 +66,126 @@ def load_int_peak(sm_mhz_max, sms=148):
     return sms * 64 * sm_mhz_max * 1e6, "nominal 148 SM x 64 IMAD/clk x max SM clock"
 
 
+FUSED_KERNEL = {0: "k_polymul_tma<0>", 1: "k_polymul_tma<1>", 2: "k_polymul_tma<2>", 3: "k_polymul_pair"}
+
+
+def newest_ncu(kernel_substr):
+    """Newest committed ncu summary (profiles/ncu_*.json, written by tools/ncu_summary.py) of a kernel: returns
+    {"capture", "fmaheavy_pct", "alu_pct", "fp64_pct", "issue_pct", "dram_bytes_per_launch", "duration_us"} or None.
+    Runs are ordered by their tag (…_r01t.json < …_r02a.json)."""
+    import glob
+    import re
+    best = None
+    for path in glob.glob(os.path.join(ROOT, "profiles", "ncu_*.json")):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+        except Exception:
+            continue
+        if kernel_substr not in (d.get("kernel") or ""):
+            continue
+        m = re.search(r"_r(\d+)([a-z]+)\.json$", path)
+        key = (int(m.group(1)), len(m.group(2)), m.group(2)) if m else (0, 0, "")
+        if best is None or key > best[0]:
+            best = (key, path, d)
+    if best is None:
+        return None
+    _, path, d = best
+    mt = d.get("metrics", {})
+
+    def val(k, scale=1.0):
+        try:
+            return float(mt[k]["value"]) * scale
+        except Exception:
+            return None
+    unit = lambda k: {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(mt.get(k, {}).get("unit"), 1.0)
+    rd, wr = val("dram__bytes_read.sum", unit("dram__bytes_read.sum")), val("dram__bytes_write.sum", unit("dram__bytes_write.sum"))
+    return {"capture": "profiles/" + os.path.basename(path),
+            "fmaheavy_pct": val("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+            "alu_pct": val("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+            "fp64_pct": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "issue_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "dram_bytes_per_launch": (rd + wr) if rd is not None and wr is not None else None,
+            "duration_us": val("gpu__time_duration.sum")}
+
+
+def reference_gpu_leg(o, xs, ys, zs_ours, batch):
+    """the reference's own GPU code on this box, next to `value` / `e2e`.
+      harness : the UNMODIFIED main.cu + NTT.cu (oracle/_ref/ref_gpu_b65536, only BATCH / NUM_AVE / DEBUG of
+                main.cuh:7-9 patched) run as `-speedgpu 6` = test_NTT_CT_GS_nega_gpu (NTT.cu:2358-2443); its own
+                printed metric (wall clock around pageable cudaMemcpy + 34 launches, NTT.cu:2383-2431)
+      kernels : the same 34 unmodified kernels launched from oracle/_ref/libqtref.so on device-resident operands,
+                CUDA events (kernel-only) and with the copies (the reference's convention) on a bounded sample,
+                checked against this engine's result on the same operands"""
+    import re
+    import subprocess
+    import numpy as np
+    from oracle_lib import Reference
+    out = {}
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_b%d" % batch)
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe, "-speedgpu", "6"], capture_output=True, text=True, timeout=240)
+            t = re.search(r"Time\s*:\s*([0-9.]+) ms", r.stdout)
+            th = re.search(r"Throughput\s*:\s*([0-9.]+) Multiplications", r.stdout)
+            out["harness"] = {"command": "oracle/_ref/ref_gpu_b%d -speedgpu 6" % batch, "rc": r.returncode,
+                              "ms_per_batch": float(t.group(1)) if t else None, "value": float(th.group(1)) if th else None,
+                              "unit": UNIT, "batch": batch,
+                              "what": "unmodified reference main.cu/NTT.cu, test_NTT_CT_GS_nega_gpu; its own printed metric "
+                                      "(host wall clock incl. pageable H2D/D2H, NUM_AVE 5)"}
+        except Exception as ex:
+            out["harness"] = {"error": str(ex)}
+    else:
+        out["harness"] = {"unavailable": "oracle/_ref/ref_gpu_b%d not built (needs /root/reference at build time)" % batch}
+    if Reference.available() and hasattr(Reference().lib, "qtref_gpu_ct_gs"):
+        ref = Reference()
+        sample = xs.size // ref.n
+        z, kernel_ms, total_ms = ref.gpu_ct_gs(xs, ys, reps=3)
+        out["kernels"] = {"sample_polymuls": sample, "kernel_only_ms": kernel_ms, "with_copies_ms": total_ms,
+                          "kernel_only_value": sample / (kernel_ms * 1e-3), "with_copies_value": sample / (total_ms * 1e-3),
+                          "unit": UNIT, "launches_per_product_batch": 34, "equals_this_engine": bool(np.array_equal(z, zs_ours)),
+                          "what": "the reference's unmodified __global__ kernels in the launch order of NTT.cu:2388-2425 "
+                                  "(oracle/_ref/libqtref.so), CUDA events"}
+    return out
+
+
+def cpu_baselines_all_sets(o, budget_s=4.0):
+    """SURVEY.md 8d-ii / BASELINE.md: the qTESLA-style C path (Montgomery reduce with PARAM_QINV, merged twiddles,
+    lazy ranges — oracle/qt_cpu_fast.c, "restatement, qTESLA source unavailable") for every parameter set on all
+    host threads, beside the slower reference-structured port (`% q`, Phi passes).  Bounded: ~budget_s per set."""
+    threads = host_threads()
+    out = []
+    for name, sid in SETS.items():
+        p = o.params(sid)
+        cal = 64 * threads
+        x = o.splitmix(1, 0, p.q, cal * p.n)
+        y = o.splitmix(2, 0, p.q, cal * p.n)
+        o.fast_polymul(sid, x, y, threads)
+        t0 = time.perf_counter()
+        o.fast_polymul(sid, x, y, threads)
+        rate = cal / (time.perf_counter() - t0)
+        count = int(max(cal, min(DEFAULT_BATCH[sid], rate * budget_s)))
+        x = o.splitmix(1, 0, p.q, count * p.n)
+        y = o.splitmix(2, 0, p.q, count * p.n)
+        t0 = time.perf_counter()
+        z = o.fast_polymul(sid, x, y, threads)
+        dt = time.perf_counter() - t0
+        one = min(count, 2048)
+        t1 = time.perf_counter()
+        o.fast_polymul(sid, x[: one * p.n], y[: one * p.n], 1)
+        dt1 = time.perf_counter() - t1
+        chk = min(count, 64)
+        t2 = time.perf_counter()
+        zp = o.polymul(sid, x[: chk * p.n], y[: chk * p.n])
+        dt2 = time.perf_counter() - t2
+        import numpy as np
+        out.append({"param_set": name, "n": int(p.n), "q": int(p.q), "value": count / dt, "unit": UNIT, "cores": threads,
+                    "kind": "port", "what": "qTESLA-style Montgomery / merged-twiddle C restatement (oracle/qt_cpu_fast.c)",
+                    "sample": f"{count} polymuls of the bench stream, {threads} threads, {dt:.2f} s", "value_1thread": one / dt1,
+                    "reference_structured_port_1thread": chk / dt2, "equals_port": bool(np.array_equal(z[: chk * p.n], zp))})
+    return out
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the GPU is busy."""
 
@@ -221,6 +341,136 @@ def cpu_baseline(set_id, o):
     }
 
 
+def inproc_multi_leg(qt, o, set_id, per_gpu):
+    """e2e through the IN-PROCESS multi-GPU entry point of the C ABI (qt_multi_polymul_host) on all visible GPUs:
+    one NUMA-bound host thread + context per GPU, contiguous shards, no collective; pinned host arrays."""
+    import ctypes as C
+    import numpy as np
+    g = qt.device_count()
+    p = qt.get_params(set_id)
+    B = per_gpu * g
+    words = B * p.n
+    ptrs, arrs = [], []
+    for _ in range(3):
+        ptr = C.c_void_p()
+        if qt.lib().qt_host_alloc(words * 4, C.byref(ptr)) != 0:
+            for q_ in ptrs:
+                qt.lib().qt_host_free(q_)
+            return {"error": "pinned allocation failed"}
+        ptrs.append(ptr)
+        arrs.append(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(words,)))
+    x, y, z = arrs
+    blk = 256 * p.n  # one random block of the bench stream tiled over the batch (host-side fill time, not traffic, is saved)
+    bx, by = o.splitmix(1, 0, p.q, blk), o.splitmix(2, 0, p.q, blk)
+    for i in range(0, words, blk):
+        x[i:i + blk] = bx
+        y[i:i + blk] = by
+    m = qt.MultiEngine(set_id, g)
+    for _ in range(2):
+        m.polymul_host(x, y, z, B)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m.polymul_host(x, y, z, B)
+    dt = (time.perf_counter() - t0) / reps
+    ok = True
+    for s_ in range(g):  # first and last polynomials of every shard
+        lo, hi = B * s_ // g, B * (s_ + 1) // g
+        for a in (lo, hi - 2):
+            sl = slice(a * p.n, (a + 2) * p.n)
+            ok &= bool(np.array_equal(z[sl], o.polymul(set_id, x[sl].copy(), y[sl].copy())))
+    m.close()
+    for q_ in ptrs:
+        qt.lib().qt_host_free(q_)
+    return {"value": B / dt, "unit": UNIT, "n_gpus": g, "batch_total": B, "ms_per_call": dt * 1e3, "parity_ok": ok,
+            "h2d_bytes_per_step": 2 * words * 4, "d2h_bytes_per_step": words * 4,
+            "api": "qt_multi_polymul_host (one process, one NUMA-bound host thread + context per GPU, contiguous shards)"}
+
+
+def batch_sweep_leg(qt, torch, stream, dev, local_rank, peaks):
+    """BASELINE.json configs[4]: n=1024 (qTESLA-III), batch 2^10 .. 2^22 on this GPU, device-resident, CUDA events."""
+    eng = qt.Engine(1, local_rank)
+    eng.set_stream(stream.cuda_stream)
+    n = eng.n
+    rows = []
+    free = torch.cuda.mem_get_info(dev)[0]
+    for lg in range(10, 23):
+        B = 1 << lg
+        if 3 * B * n * 4 > free * 0.9:
+            break
+        x = torch.empty(B * n, dtype=torch.int32, device=dev)
+        y = torch.empty_like(x)
+        z = torch.empty_like(x)
+        steps = max(5, min(200, (1 << 23) // B))
+        with torch.cuda.stream(stream):
+            eng.fill_uniform(x, 1, 0)
+            eng.fill_uniform(y, 2, 0)
+            for _ in range(3):
+                eng.polymul(x, y, z, B)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                eng.polymul(x, y, z, B)
+            e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        rows.append({"batch": B, "us_per_launch": ms * 1e3, "value": B / (ms * 1e-3), "working_set_MiB": 3 * B * n * 4 >> 20})
+        del x, y, z
+    eng.close()
+    return {"param_set": "qTESLA-III", "n": n, "unit": UNIT, "rows": rows,
+            "note": "batches below ~16 Ki polynomials fit the 126 MB L2 (working set column) and are launch-bound, not HBM- or pipe-bound"}
+
+
+def small_batch_leg(qt, torch, stream, dev, local_rank):
+    """Launch-bound batches: a chain of 100 dependent fused launches (z_k+1 = z_k * y), once as 100 host launches on
+    the stream (programmatic dependent launch on), once as ONE replay of a CUDA graph recorded with
+    qt_graph_begin / qt_graph_end.  us per product launch."""
+    eng = qt.Engine(1, local_rank)
+    eng.set_stream(stream.cuda_stream)
+    n, K = eng.n, 100
+    rows = []
+    for B in (256, 1024, 2048, 4096):
+        x = torch.empty(B * n, dtype=torch.int32, device=dev)
+        y = torch.empty_like(x)
+        bufs = [torch.empty_like(x), torch.empty_like(x)]
+
+        def chain():
+            src = x
+            for k in range(K):
+                eng.polymul(src, y, bufs[k & 1], B)
+                src = bufs[k & 1]
+
+        def timed(fn, reps=10):
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    fn()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(reps):
+                    fn()
+                e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) / reps / K * 1e3
+        with torch.cuda.stream(stream):
+            eng.fill_uniform(x, 1, 0)
+            eng.fill_uniform(y, 2, 0)
+        stream.synchronize()
+        us_stream = timed(chain)
+        eng.graph_begin()
+        chain()
+        g = eng.graph_end()
+        us_graph = timed(lambda: eng.graph_launch(g))
+        eng.graph_destroy(g)
+        rows.append({"batch": B, "us_per_launch_stream": us_stream, "us_per_launch_graph": us_graph,
+                     "value_stream": B / (us_stream * 1e-6), "value_graph": B / (us_graph * 1e-6)})
+        del x, y, bufs
+    eng.close()
+    return {"param_set": "qTESLA-III", "chain_length": K, "unit": UNIT, "rows": rows,
+            "api": "qt_graph_begin / qt_graph_end / qt_graph_launch (CUDA graph of the caller's launch sequence)"}
+
+
 _REAL_STDOUT = None
 
 
@@ -252,7 +502,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the other parameter sets / CPU baseline")
     ap.add_argument("--launch-overlap", type=int, default=0, choices=[0, 1, 2],
                     help="programmatic dependent launch of the fused kernel: 0 automatic (on), 1 never, 2 always")
-    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3],
+    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="fused-kernel data path: 0 automatic, 1 direct coalesced loads, 2 TMA-staged")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -341,14 +591,8 @@ def main():
     hbm_achieved = per_gpu_rate * bytes_pp / 1e9
     int_peak, int_src = load_int_peak(float(peaks.get("sm_max_mhz", 1965.0)))
     int_achieved = per_gpu_rate * slots_pp
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_fused.json")
-    if os.path.exists(tpath):
-        try:
-            with open(tpath) as f:
-                traffic = json.load(f).get(args.set)
-        except Exception:
-            traffic = None
+    ncu_main = newest_ncu(FUSED_KERNEL[set_id])  # newest committed ncu --set full summary of this kernel
+    traffic = ncu_main["dram_bytes_per_launch"] if ncu_main else None
 
     # parity check of the timed buffers against the oracle on EVERY rank: 1024 polynomials incl. the first
     # and last of the rank's shard, and the shard's slice of the synthetic stream
@@ -361,6 +605,13 @@ def main():
     gen_ok = bool(np.array_equal(xs[: p.n], o.splitmix(1, first, p.q, p.n)))
     par_ok = bool(np.array_equal(zs, o.polymul(set_id, xs, ys, threads=max(1, host_threads() // world)))) and gen_ok
     parity = max_over_ranks(0.0 if par_ok else 1.0) == 0.0
+
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_extras and set_id == 1 and batch == DEFAULT_BATCH[1]:
+        try:
+            ref_gpu = reference_gpu_leg(o, xs, ys, zs, batch)
+        except Exception as ex:  # the baseline leg must never take the bench down
+            ref_gpu = {"error": str(ex)}
 
     # end-to-end: host buffers through qt_polymul_host (H2D + kernel + D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, 10))
@@ -401,8 +652,15 @@ def main():
 
     extras = []
     cpu = None
+    cpu_all = None
+    e2e_inproc = None
+    sweep = None
+    small = None
     if rank == 0 and world == 1 and not args.no_extras:
         del hx, hy, hz
+        e2e_inproc = inproc_multi_leg(qt, o, set_id, batch)
+        sweep = batch_sweep_leg(qt, torch, stream, dev, local_rank, peaks)
+        small = small_batch_leg(qt, torch, stream, dev, local_rank)
         for name, sid in SETS.items():
             if sid == set_id:
                 continue
@@ -410,13 +668,17 @@ def main():
             st = max(3, min(args.steps, 50))
             b2, _, _, i2 = algorithmic_counts(e2.params.n, e2.params.logn)
             r2 = DEFAULT_BATCH[sid] * st / (ms2 * 1e-3)
+            nc = newest_ncu(FUSED_KERNEL[sid])
             extras.append({"param_set": name, "n": int(e2.params.n), "batch": DEFAULT_BATCH[sid], "value": r2, "unit": UNIT,
-                           "hbm_frac": r2 * b2 / 1e9 / float(peaks["hbm_gbs"]), "int_frac": r2 * i2 / int_peak})
+                           "hbm_frac": r2 * b2 / 1e9 / float(peaks["hbm_gbs"]), "int_frac": r2 * i2 / int_peak,
+                           "int_frac_unit": "multiply-pipe slots (mul.lo 1, mul.hi/wide 2), 4 per modular multiply",
+                           "kernel": FUSED_KERNEL[sid], "ncu_fmaheavy_pct": nc["fmaheavy_pct"] if nc else None,
+                           "ncu_capture": nc["capture"] if nc else None})
             e2.close()
         st = max(3, min(args.steps, 50))
         variants = {}
-        for vname, v in (("direct_loads", 1), ("tma_staged", 2), ("split_tile_n2048", 3)):
-            if v == 3 and p.n != 2048:
+        for vname, v in (("direct_loads", 1), ("tma_staged", 2), ("split_tile_n2048", 3), ("split_tile_two_warps_n2048", 4)):
+            if v >= 3 and p.n != 2048:
                 continue  # the split tile exists for n = 2048 only
             try:
                 e2, _, ms2, _ = run_config(set_id, batch, st, 3, variant=v)
@@ -425,12 +687,33 @@ def main():
             except Exception as ex:  # e.g. variant unsupported for this shape
                 variants[vname] = str(ex)
         nuss = {}
-        # Z_q row products: schoolbook (the reference's structure) and recursive (split once more); "mod_q" = automatic
-        for rname, ring, nv in (("ring_2p32m1", qt.RING_2P32M1, 0), ("mod_q", qt.RING_MODQ, 0),
-                                ("mod_q_schoolbook_rows", qt.RING_MODQ, 1), ("mod_q_recursive_rows", qt.RING_MODQ, 2)):
+        # Z_q row products: schoolbook (the reference's structure), recursive (split once more), FP64-pipe schoolbook;
+        # "mod_q" = automatic.  pipe_frac: algorithmic row-product multiplies (2m*r^2 = 65 536 wide
+        # multiplies per n=1024 product; the recursive form needs 2m * 2MI * RI^2) against the pipe that executes them:
+        # a 32x32->64 multiply-add occupies the integer multiply pipe for 2 slots; the FP64 form issues one DFMA each
+        # (64 lanes/clk/SM, the same peak rate as mad.lo).
+        m_, r_ = (16, 32) if p.n == 512 else (32, p.n // 32)
+        mi_, ri_ = (8, 8) if r_ == 64 else (4, 8)
+        school_mults, rec_mults = 2 * m_ * r_ * r_, 2 * m_ * 2 * mi_ * ri_ * ri_
+        small_q = p.q < (1 << 25)
+        nuss_defs = (("ring_2p32m1", qt.RING_2P32M1, 0, school_mults, 2, "k_nussbaumer_warp<1, 0, 0>"),
+                     ("mod_q", qt.RING_MODQ, 0, school_mults if small_q else rec_mults, 1 if small_q else 2, None),
+                     ("mod_q_schoolbook_rows", qt.RING_MODQ, 1, school_mults, 2, "k_nussbaumer_warp<1, 1, 0>"),
+                     ("mod_q_recursive_rows", qt.RING_MODQ, 2, rec_mults, 2, "k_nussbaumer_warp<1, 1, 1>"),
+                     ("mod_q_fp64_rows", qt.RING_MODQ, 3, school_mults, 1, "k_nussbaumer_warp<1, 1, 2>"),
+                     ("ring_2p32m1_lift_q (sparse / small operands, exact under its precondition)", qt.RING_2P32M1_LIFT_Q, 0,
+                      school_mults, 2, None))
+        for rname, ring, nv, mults, slots, kname in nuss_defs:
             try:
-                e2, _, ms2, _ = run_config(set_id, batch, max(3, min(args.steps, 10)), 3, nuss_ring=ring, nuss_variant=nv)
-                nuss[rname] = batch * max(3, min(args.steps, 10)) / (ms2 * 1e-3)
+                st_n = max(3, min(args.steps, 10))
+                e2, _, ms2, _ = run_config(set_id, batch, st_n, 3, nuss_ring=ring, nuss_variant=nv)
+                rate = batch * st_n / (ms2 * 1e-3)
+                nc = newest_ncu(kname) if (kname and set_id == 1) else None
+                nuss[rname] = {"value": rate, "unit": UNIT, "row_product_multiplies_per_polymul": mults,
+                               "pipe": "fp64 (DFMA)" if slots == 1 else "integer multiply (IMAD.WIDE = 2 slots)",
+                               "pipe_frac": rate * mults * slots / int_peak,
+                               "ncu_fmaheavy_pct": nc["fmaheavy_pct"] if nc else None, "ncu_fp64_pct": nc["fp64_pct"] if nc else None,
+                               "ncu_capture": nc["capture"] if nc else None}
                 e2.close()
             except Exception as ex:
                 nuss[rname] = str(ex)
@@ -468,6 +751,7 @@ def main():
         e2.close()
         from oracle_lib import Oracle
         cpu = cpu_baseline(set_id, Oracle())
+        cpu_all = cpu_baselines_all_sets(Oracle())
 
     if rank == 0:
         line = {
@@ -482,8 +766,11 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                          "frac": hbm_achieved / float(peaks["hbm_gbs"]), "traffic": traffic,
+                         "traffic_source": (ncu_main["capture"] + ": dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full")
+                         if ncu_main else None,
                          "peak_source": peaks_src, "kernel": ("k_polymul" if eng.kernel_info()["block"] == 256 else
-                                                                  "k_polymul_split" if (p.n == 2048 and args.variant in (0, 3)) else "k_polymul_tma"),
+                                                                  "k_polymul_pair" if (p.n == 2048 and args.variant in (0, 4)) else
+                                                                  "k_polymul_split" if (p.n == 2048 and args.variant == 3) else "k_polymul_tma"),
                          "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_pp * batch,
                          "binding": "int_mul_pipe", "binding_frac": int_achieved / int_peak,
@@ -494,6 +781,8 @@ def main():
                              "peak_source": int_src, "algorithmic_slots_per_polymul": slots_pp,
                              "algorithmic_mul_instr_per_polymul": imad_pp,
                              "frac_survey_definition": per_gpu_rate * imad_pp / int_peak,
+                             "ncu_fmaheavy_pct": ncu_main["fmaheavy_pct"] if ncu_main else None,
+                             "ncu_capture": ncu_main["capture"] if ncu_main else None,
                              "note": "binding roofline; compare with ncu sm__pipe_fmaheavy_cycles_active in profiles/"},
             "parity_check": {"ok": parity, "polynomials_per_rank": 2 * min(512, batch // 2), "ranks_checked": world,
                              "against": "CPU oracle (oracle/qt_oracle.c)"},
@@ -504,6 +793,16 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if cpu_all is not None:
+            line["cpu_baseline_all_sets"] = cpu_all
+        if ref_gpu is not None:
+            line["reference_gpu"] = ref_gpu
+        if e2e_inproc is not None:
+            line["e2e_inproc_multi"] = e2e_inproc
+        if sweep is not None:
+            line["batch_sweep"] = sweep
+        if small is not None:
+            line["small_batch_chains"] = small
         if extras:
             line["other_configs"] = extras
             line["fused_variants"] = variants

@@ -96,12 +96,15 @@ int qt_set_stream(qt_ctx* ctx, void* cuda_stream);
 int qt_synchronize(qt_ctx* ctx);
 /* fused-kernel data path: 0 = automatic, 1 = direct coalesced loads, 2 = TMA bulk copies staged
  * through shared memory with an mbarrier (needs 16-byte aligned operands), 3 = n=2048 only: TMA-staged
- * with the polynomial processed as two 1024-point halves (what "automatic" picks for qTESLA-p-III) */
+ * with the polynomial processed as two 1024-point halves by one warp, 4 = n=2048 only: the same two halves by a
+ * PAIR of warps side by side (what "automatic" picks for qTESLA-p-III) */
 int qt_set_fused_variant(qt_ctx* ctx, int variant);
 /* row products of the Z_q Nussbaumer kernels: 0 = automatic, 1 = schoolbook (the structure of the reference's
  * `naive`, NTT.cu:147-165), 2 = recursive (the 2m length-r products are split once more, 32 = 4*8 / 64 = 8*8),
  * 3 = schoolbook on the FP64 pipe with exact double-precision accumulation (q < 2^25 only, else
- * QT_ERR_UNSUPPORTED).  Results are identical; the ring 2^32-1 always uses the reference's schoolbook order. */
+ * QT_ERR_UNSUPPORTED).  Results are identical; the ring 2^32-1 always uses the reference's schoolbook order.
+ * + 16 (flag): the whole-polynomial kernels instead of the block-pass warp kernel that serves n = 1024 / 2048 by
+ * default (kept for A/B measurements; results are identical). */
 int qt_set_nussbaumer_variant(qt_ctx* ctx, int variant);
 /* Programmatic dependent launch of the TMA-staged kernels: the set-up of a launch (barriers, twiddle table) overlaps
  * the tail of the previous kernel of the stream; operands are touched only after that kernel has completed.

@@ -15,7 +15,7 @@ SOURCES = [os.path.join(CSRC, f) for f in ("qt_capi.cu", "qt_host.cu", "qt_refer
 HEADERS = [os.path.join(CSRC, f) for f in
            ("qt_params.h", "qt_tables.h", "qt_tile.cuh", "qt_kernels.cuh", "qt_nussbaumer.cuh")] + [
     os.path.join(INCLUDE, "qtesla_b200.h"), os.path.join(INCLUDE, "qtesla_b200_reference_api.h")]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-diag-suppress=128", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 
 
@@ -35,11 +35,21 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """QT_NVCC_EXTRA="-DQT_...=..." QT_BUILD_TAG=name builds an A/B variant into build_ab/name/libqtesla_b200.so
+    (select it at run time with QT_LIB_PATH); without a tag the product library next to this file is (re)built."""
+    global OBJ_DIR, LIB
+    tag = os.environ.get("QT_BUILD_TAG")
+    extra = os.environ.get("QT_NVCC_EXTRA", "").split()  # A/B builds: -DQT_...=...
+    if tag:
+        OBJ_DIR = os.path.join(os.path.dirname(PKG_DIR), "build_ab", tag)
+        LIB = os.path.join(OBJ_DIR, "libqtesla_b200.so")
+        force = True
+    elif extra:
+        raise SystemExit("QT_NVCC_EXTRA without QT_BUILD_TAG would overwrite the product library with an A/B variant")
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ_DIR, exist_ok=True)
-    extra = os.environ.get("QT_NVCC_EXTRA", "").split()  # A/B builds: -DQT_...=...
 
     def compile_one(src):
         obj = _obj(src)

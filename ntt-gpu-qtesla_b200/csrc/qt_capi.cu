@@ -29,6 +29,9 @@ using namespace qt;
 #ifndef QT_AUTO_PREFERS_TMA
 #define QT_AUTO_PREFERS_TMA 1
 #endif
+#ifndef QT_AUTO_PREFERS_PAIR
+#define QT_AUTO_PREFERS_PAIR 1  // n = 2048: two warps per polynomial (k_polymul_pair) rather than one (k_polymul_split)
+#endif
 
 #define QT_CUDA(call)                                \
     do {                                             \
@@ -48,6 +51,7 @@ struct qt_ctx {
     int occ_fused = 0, occ_tma = 0, tma_warps = 0;
     TwQuad* d_tab_split = nullptr;          // n=2048 only: tables of the split tile (k_polymul_split)
     bool split_ok = false;
+    bool pair_ok = false;                   // n=2048 only: two warps per polynomial (k_polymul_pair)
     int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged, 3 split tile (n=2048)
     int nuss_variant = 0;  // 0 auto, 1 schoolbook row products, 2 recursive row products (Z_q)
     int overlap = 0;       // programmatic dependent launch: 0 auto (non-blocking streams only), 1 never, 2 always
@@ -181,6 +185,11 @@ int upload_tables(qt_ctx* c) {
             c->split_ok = occ > 0;
         else
             (void)cudaGetLastError();
+        if (c->split_ok && cudaFuncSetAttribute(k_polymul_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairShape::SMEM) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polymul_pair, PairShape::PAIRS * 64, PairShape::SMEM) == cudaSuccess)
+            c->pair_ok = occ > 0;
+        else
+            (void)cudaGetLastError();
     }
     switch (c->set) {
     case SET_I: return setup_set<SET_I>(c, T);
@@ -233,18 +242,45 @@ static cudaError_t launch_pdl(qt_ctx* c, int known, void (*kern)(KArgs...), int 
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Launch geometry of the TMA-staged kernels for `tiles` warp tiles: grid = min(#SMs, tiles) CTAs of just enough warps
+// (<= max_warps).  Small batches therefore take less shared memory per CTA (table block + 2 buffers + 2 barriers per
+// warp), and the CTA of the NEXT launch of the stream fits on the SM beside a running one: with programmatic dependent
+// launch its prologue (barrier set-up, twiddle-table copy) then overlaps the predecessor's arithmetic.
+struct StageGeom { int grid, warps; size_t smem; };
+static StageGeom stage_geom(const qt_ctx* c, size_t tiles, int max_warps, size_t table_bytes, size_t warp_bytes, size_t extra = 0) {
+    StageGeom g;
+    g.grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
+    g.warps = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_warps, (tiles + g.grid - 1) / g.grid));
+    g.smem = table_bytes + (size_t)g.warps * warp_bytes + extra;
+    return g;
+}
+template <int SET> static StageGeom stage_geom_set(const qt_ctx* c, size_t tiles, size_t extra = 0) {
+    using G = StageShape<SET>;
+    return stage_geom(c, tiles, TmaCfg<SET>::WARPS, KernelShape<SET>::TW_BYTES, G::BUFS * G::WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t), extra);
+}
+static StageGeom stage_geom_split(const qt_ctx* c, size_t tiles, size_t extra = 0) {
+    return stage_geom(c, tiles, SplitShape::WARPS, SplitShape::TW_BYTES, 2 * SplitShape::WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t), extra);
+}
+
 template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t B,
                                       cudaStream_t s, int known = OVL_PROBE) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
     const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;  // bulk copies need 16-byte alignment
     const bool tma = c->occ_tma > 0 && aligned && (c->variant == 2 || (c->variant == 0 && QT_AUTO_PREFERS_TMA));
-    if (SET == SET_P_III && c->split_ok && aligned && (c->variant == 3 || c->variant == 0)) {
-        cudaError_t e = launch_pdl(c, known, k_polymul_split<0>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B)),
-                                   SplitShape::WARPS * 32, SplitShape::SMEM, s, x, y, z, B, c->d_tab_split);
+    if (SET == SET_P_III && c->pair_ok && aligned && (c->variant == 4 || (c->variant == 0 && QT_AUTO_PREFERS_PAIR))) {
+        // two warps per polynomial; grid = min(#SMs, B) CTAs of just enough pairs
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, B));
+        const int pairs = (int)std::max<size_t>(1, std::min<size_t>((size_t)PairShape::PAIRS, (B + grid - 1) / grid));
+        cudaError_t e = launch_pdl(c, known, k_polymul_pair, grid, pairs * 64,
+                                   PairShape::TW_BYTES + (size_t)pairs * PairShape::PAIR_BYTES, s, x, y, z, B, c->d_tab_split);
+        if (e != cudaSuccess) return (int)e;
+    } else if (SET == SET_P_III && c->split_ok && aligned && (c->variant == 3 || c->variant == 0)) {
+        const StageGeom g = stage_geom_split(c, B);
+        cudaError_t e = launch_pdl(c, known, k_polymul_split<0>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab_split);
         if (e != cudaSuccess) return (int)e;
     } else if (tma) {
-        cudaError_t e = launch_pdl(c, known, k_polymul_tma<SET>, (int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_tma, tiles)),
-                                   TmaCfg<SET>::WARPS * 32, c->smem_tma, s, x, y, z, B, c->d_tab[1]);
+        const StageGeom g = stage_geom_set<SET>(c, tiles);
+        cudaError_t e = launch_pdl(c, known, k_polymul_tma<SET>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab[1]);
         if (e != cudaSuccess) return (int)e;
     }
     else
@@ -258,37 +294,37 @@ template <int SET> int launch_polymul_ntt(qt_ctx* c, const uint32_t* ahat, bool 
     if (c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
     if ((((uintptr_t)ahat | (uintptr_t)y) & 15) != 0) return QT_ERR_BAD_ARG;  // 128-bit / bulk-copy alignment
     if (SET == SET_P_III && c->split_ok && c->variant != 2) {
-        const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, (size_t)B));
-        const cudaError_t e = bcast ? launch_pdl(c, OVL_PROBE, k_polymul_split<1>, g, SplitShape::WARPS * 32, SplitShape::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab_split)
-                                    : launch_pdl(c, OVL_PROBE, k_polymul_split<2>, g, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, ahat, y, z, B, c->d_tab_split);
+        const StageGeom g = stage_geom_split(c, B, bcast ? SplitShape::WORDS * sizeof(uint32_t) : 0);
+        const cudaError_t e = bcast ? launch_pdl(c, OVL_PROBE, k_polymul_split<1>, g.grid, g.warps * 32, g.smem, c->stream, ahat, y, z, B, c->d_tab_split)
+                                    : launch_pdl(c, OVL_PROBE, k_polymul_split<2>, g.grid, g.warps * 32, g.smem, c->stream, ahat, y, z, B, c->d_tab_split);
         if (e != cudaSuccess) return (int)e;
         c->launches++;
         return (int)cudaGetLastError();
     }
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
-    const cudaError_t e = bcast ? launch_pdl(c, OVL_PROBE, k_polymul_ntt<SET, true>, grid, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM_BCAST, c->stream, ahat, y, z, B, c->d_tab[1])
-                                : launch_pdl(c, OVL_PROBE, k_polymul_ntt<SET, false>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, ahat, y, z, B, c->d_tab[1]);
+    const StageGeom g = stage_geom_set<SET>(c, tiles, bcast ? Cfg<SET>::N * sizeof(uint32_t) : 0);
+    const cudaError_t e = bcast ? launch_pdl(c, OVL_PROBE, k_polymul_ntt<SET, true>, g.grid, g.warps * 32, g.smem, c->stream, ahat, y, z, B, c->d_tab[1])
+                                : launch_pdl(c, OVL_PROBE, k_polymul_ntt<SET, false>, g.grid, g.warps * 32, g.smem, c->stream, ahat, y, z, B, c->d_tab[1]);
     if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <int SET, bool INV> int launch_ntt_tma(qt_ctx* c, uint32_t* a, size_t B) {
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, tiles));
-    const cudaError_t e = launch_pdl(c, OVL_PROBE, k_ntt_tma<SET, INV>, grid, TmaCfg<SET>::WARPS * 32, c->smem_tma, c->stream, a, B, c->d_tab[0]);
+    const StageGeom g = stage_geom_set<SET>(c, tiles);
+    const cudaError_t e = launch_pdl(c, OVL_PROBE, k_ntt_tma<SET, INV>, g.grid, g.warps * 32, g.smem, c->stream, a, B, c->d_tab[0]);
     if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <bool INV> int launch_ntt_split(qt_ctx* c, uint32_t* a, size_t B) {
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->num_sms, B));
-    const cudaError_t e = launch_pdl(c, OVL_PROBE, k_ntt_split<INV>, grid, SplitShape::WARPS * 32, SplitShape::SMEM, c->stream, a, B, c->d_tab_split);
+    const StageGeom g = stage_geom_split(c, B);
+    const cudaError_t e = launch_pdl(c, OVL_PROBE, k_ntt_split<INV>, g.grid, g.warps * 32, g.smem, c->stream, a, B, c->d_tab_split);
     if (e != cudaSuccess) return (int)e;
     c->launches++;
     return (int)cudaGetLastError();
 }
 template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
-    if (SET == SET_P_III && c->split_ok && (c->variant == 0 || c->variant == 3) && ((uintptr_t)a & 15) == 0)
+    if (SET == SET_P_III && c->split_ok && c->variant != 1 && c->variant != 2 && ((uintptr_t)a & 15) == 0)
         return launch_ntt_split<false>(c, a, B);
     if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, false>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
@@ -297,7 +333,7 @@ template <int SET> int launch_forward(qt_ctx* c, uint32_t* a, size_t B) {
     return (int)cudaGetLastError();
 }
 template <int SET> int launch_inverse(qt_ctx* c, uint32_t* a, size_t B) {
-    if (SET == SET_P_III && c->split_ok && (c->variant == 0 || c->variant == 3) && ((uintptr_t)a & 15) == 0)
+    if (SET == SET_P_III && c->split_ok && c->variant != 1 && c->variant != 2 && ((uintptr_t)a & 15) == 0)
         return launch_ntt_split<true>(c, a, B);
     if (c->occ_tma > 0 && c->variant != 1 && ((uintptr_t)a & 15) == 0) return launch_ntt_tma<SET, true>(c, a, B);
     const size_t tiles = (B + Cfg<SET>::PPW - 1) / Cfg<SET>::PPW;
@@ -522,9 +558,10 @@ int qt_set_stream(qt_ctx* c, void* s) {
 }
 
 int qt_set_fused_variant(qt_ctx* c, int variant) {
-    if (!c || variant < 0 || variant > 3) return QT_ERR_BAD_ARG;
+    if (!c || variant < 0 || variant > 4) return QT_ERR_BAD_ARG;
     if (variant == 2 && c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
     if (variant == 3 && !c->split_ok) return QT_ERR_UNSUPPORTED;
+    if (variant == 4 && !c->pair_ok) return QT_ERR_UNSUPPORTED;
     c->variant = variant;
     return 0;
 }
@@ -536,8 +573,8 @@ int qt_set_launch_overlap(qt_ctx* c, int mode) {
 }
 
 int qt_set_nussbaumer_variant(qt_ctx* c, int variant) {
-    if (!c || variant < NUSS_AUTO || variant > NUSS_FP64) return QT_ERR_BAD_ARG;
-    if (variant == NUSS_FP64 && !QT_DISPATCH(c, nuss_has_f64)) return QT_ERR_UNSUPPORTED;
+    if (!c || (variant & ~NUSS_WHOLE) < NUSS_AUTO || (variant & ~NUSS_WHOLE) > NUSS_FP64) return QT_ERR_BAD_ARG;
+    if ((variant & ~NUSS_WHOLE) == NUSS_FP64 && !QT_DISPATCH(c, nuss_has_f64)) return QT_ERR_UNSUPPORTED;
     c->nuss_variant = variant;
     return 0;
 }
@@ -949,6 +986,14 @@ int qt_launch_count(qt_ctx* c, uint64_t* out) {
 
 int qt_kernel_info(qt_ctx* c, int* grid, int* block, int* smem, int* per_sm, int* sms) {
     if (!c) return QT_ERR_BAD_ARG;
+    if (c->pair_ok && (c->variant == 4 || (c->variant == 0 && QT_AUTO_PREFERS_PAIR))) {
+        if (grid) *grid = c->num_sms;
+        if (block) *block = PairShape::PAIRS * 64;
+        if (smem) *smem = (int)PairShape::SMEM;
+        if (per_sm) *per_sm = 1;
+        if (sms) *sms = c->num_sms;
+        return 0;
+    }
     if (c->split_ok && (c->variant == 3 || c->variant == 0)) {
         if (grid) *grid = c->num_sms;
         if (block) *block = SplitShape::WARPS * 32;

@@ -148,12 +148,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy accesses of this thread are ordered before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// A/B switch: write z with ONE bulk copy per tile from a third per-warp shared-memory buffer
+// (cp.async.bulk.global.shared::cta) instead of 32 coalesced 32-bit global stores per thread.
+#ifndef QT_TMA_STORE
+#define QT_TMA_STORE 0
+#endif
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 template <int SET> struct StageShape {
     using T = Tile<SET>;
     static constexpr uint32_t PAD = (T::PPW == 2) ? 16 : 0;  // de-conflicts the rows of the two polynomials
     static constexpr uint32_t POLY_STRIDE = T::N + PAD;      // words
     static constexpr uint32_t WORDS = T::PPW * POLY_STRIDE;  // one buffer (>= TILE_WORDS)
-    static constexpr size_t SMEM = KernelShape<SET>::TW_BYTES + (size_t)TmaCfg<SET>::WARPS * 2 * WORDS * sizeof(uint32_t) +
+    static constexpr uint32_t BUFS = 2 + QT_TMA_STORE;       // x staging, y staging (+ z staging for the bulk-store variant)
+    static constexpr size_t SMEM = KernelShape<SET>::TW_BYTES + (size_t)TmaCfg<SET>::WARPS * BUFS * WORDS * sizeof(uint32_t) +
                                    (size_t)TmaCfg<SET>::WARPS * 2 * sizeof(uint64_t);
     static constexpr size_t SMEM_BCAST = SMEM + T::N * sizeof(uint32_t);  // + the broadcast a_hat of k_polymul_ntt
     static __device__ __forceinline__ uint32_t off(uint32_t lane, uint32_t r) {
@@ -170,11 +182,11 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
     extern __shared__ uint4 smem_raw[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
-    constexpr int NW = TmaCfg<SET>::WARPS;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
+    const int NW = (int)(blockDim.x >> 5);  // <= TmaCfg<SET>::WARPS; small batches are launched with fewer warps (less shared memory: the next launch's CTA fits beside this one)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * G::BUFS * G::WORDS);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* A = s_stage + warp * 2 * G::WORDS;
+    uint32_t* A = s_stage + warp * G::BUFS * G::WORDS;
     uint32_t* B = A + G::WORDS;
     uint64_t* bar_a = s_bar + 2 * warp;
     uint64_t* bar_b = bar_a + 1;
@@ -245,8 +257,29 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
         __syncwarp();                     // B is free: fetch the next tile's y into it
         if (more && lane == 0) issue(y, B, bar_b, tile + stride);
         T::template inv_rows<UNI_INV_FUSED>(v, P);
+#if QT_TMA_STORE
+        {
+            uint32_t* Cz = B + G::WORDS;
+            if (lane == 0) bulk_wait_read();  // the previous tile's bulk store has read the buffer
+            __syncwarp();
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) Cz[G::off(lane, r)] = v[r];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const size_t p0 = tile * T::PPW;
+                const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);
+                for (uint32_t p = 0; p < np; p++)
+                    bulk_s2g(z + (p0 + p) * T::N, Cz + p * G::POLY_STRIDE, T::N * (uint32_t)sizeof(uint32_t));
+            }
+        }
+#else
         T::store_rows(v, z + base, lane, valid);
+#endif
     }
+#if QT_TMA_STORE
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory must outlive the copies
+#endif
 }
 
 // Fused product for n = 2048 (qTESLA-p-III) on the SPLIT tile: a polynomial is two 1024-point halves
@@ -281,7 +314,7 @@ k_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
     extern __shared__ uint4 smem_raw[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
-    constexpr int NW = G::WARPS;
+    const int NW = (int)(blockDim.x >> 5);  // <= SplitShape::WARPS
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* A = s_stage + warp * 2 * G::WORDS;
@@ -405,6 +438,129 @@ k_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
     }
 }
 
+// Fused product for n = 2048 with TWO WARPS per polynomial (run r02h).  Same split tile, same buffers per polynomial
+// as k_polymul_split<0>, but after the level that joins the halves each warp of the pair transforms ONE half, so the
+// two halves run side by side instead of one after the other: 16 resident warps per SM on the same 16 KiB of staging per
+// polynomial (the one-warp form tops out at 12), and no second half waiting in shared memory.  The pair meets at a
+// named barrier (bar.sync 1 + pair, 64) around the two places where data crosses the halves: the split level (each
+// warp computes the butterflies of 16 of the 32 register rows and leaves both outputs in the buffer) and the join at
+// the end (likewise).  One lane of the pair issues the bulk copies; both warps wait on the mbarriers.
+#ifndef QT_PAIR_P
+#define QT_PAIR_P 8  // pairs per CTA
+#endif
+struct PairShape {
+    using T = Tile<SET_P_III_H>;
+    static constexpr int PAIRS = QT_PAIR_P;
+    static constexpr uint32_t HALF = T::N, WORDS = 2 * T::N;
+    static constexpr size_t TW_BYTES = (size_t)T::TABLE_QUADS * sizeof(TwQuad);
+    static constexpr size_t PAIR_BYTES = 2 * WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t);
+    static constexpr size_t SMEM = TW_BYTES + (size_t)PAIRS * PAIR_BYTES;
+};
+__device__ __forceinline__ void pair_sync(uint32_t pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+__global__ void __launch_bounds__(PairShape::PAIRS * 64, 1)
+k_polymul_pair(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwQuad* __restrict__ g_lane) {
+    using T = PairShape::T;
+    using G = PairShape;
+    extern __shared__ uint4 smem_raw[];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
+    const int NP = (int)(blockDim.x >> 6);  // pairs in this CTA (<= PairShape::PAIRS)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NP * 2 * G::WORDS);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp >> 1, h = warp & 1;
+    uint32_t* A = s_stage + pair * 2 * G::WORDS;
+    uint32_t* B = A + G::WORDS;
+    uint64_t* bar_a = s_bar + 2 * pair;
+    uint64_t* bar_b = bar_a + 1;
+    const size_t stride = (size_t)gridDim.x * NP;
+    size_t tile = (size_t)pair * gridDim.x + blockIdx.x;  // SM-interleaved; one polynomial per tile
+    const bool issuer = h == 0 && lane == 0;
+    auto issue = [&](const uint32_t* g, uint32_t* st, uint64_t* bar, size_t t) {
+        mbar_expect_tx(bar, G::WORDS * (uint32_t)sizeof(uint32_t));
+        bulk_g2s(st, g + t * G::WORDS, G::WORDS * (uint32_t)sizeof(uint32_t), bar);
+    };
+    pdl_launch_dependents();
+    if (issuer) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    copy_table_to_smem(s_tw, g_lane, T::TABLE_QUADS);
+    pdl_wait();  // the operands may be the previous launch's output
+    if (issuer && tile < batch) {
+        issue(x, A, bar_a, tile);
+        issue(y, B, bar_b, tile);
+    }
+    __syncthreads();
+
+    constexpr uint32_t HR = T::E / 2;  // register rows of the split / join level this warp works on: [HR h, HR h + HR)
+    uint32_t phase = 0;
+    for (; tile < batch; tile += stride, phase ^= 1) {
+        const bool more = tile + stride < batch;
+        uint32_t v[T::E];
+#pragma unroll 1
+        for (int op = 0; op < 2; op++) {  // x, then y (which continues into the inverse)
+            uint32_t* st = op ? B : A;
+            mbar_wait(op ? bar_b : bar_a, phase);
+            {
+                uint32_t lo[HR], hi[HR];
+#pragma unroll
+                for (uint32_t k = 0; k < HR; k++) {
+                    lo[k] = st[lane + 32 * (HR * h + k)];
+                    hi[k] = st[G::HALF + lane + 32 * (HR * h + k)];
+                }
+                pair_sync(pair);  // every staging word has been read: the buffer becomes scratch
+#pragma unroll
+                for (uint32_t k = 0; k < HR; k++) {
+                    T::ct(lo[k], hi[k], uni_tw<SET_P_III_H, UNI_FWD>(0));
+                    const uint32_t o = T::swz(T::row_off(lane, HR * h + k));
+                    st[o] = lo[k];
+                    st[G::HALF + o] = hi[k];
+                }
+            }
+            pair_sync(pair);
+            uint32_t* sh = st + h * G::HALF;  // from here on each warp is alone with its half
+            T::lds_rows(v, sh, lane);
+            T::fwd_rows(v, 32 * h);
+            T::sts_rows(v, sh, lane);
+            __syncwarp();
+            T::lds_cols(v, sh, lane);
+            T::fwd_cols(v, s_tw + h * T::TW_QUADS + lane);
+            if (op == 0) {
+                __syncwarp();              // every lane has read its columns
+                T::sts_cols(v, sh, lane);  // NTT(x) half h; each lane reads back only what it wrote
+            }
+        }
+        T::pointwise_mont_stash(v, A + h * G::HALF, lane);
+        fence_proxy_async();
+        pair_sync(pair);  // both halves of NTT(x) are consumed: A is free, fetch the next x
+        if (more && issuer) issue(x, A, bar_a, tile + stride);
+        uint32_t* sh = B + h * G::HALF;
+        T::inv_cols(v, s_tw + (1 - h) * T::TW_QUADS + (T::BLOCKS - 1 - lane));  // mirrored table of the OTHER half
+        __syncwarp();
+        T::sts_cols(v, sh, lane);
+        __syncwarp();
+        T::lds_rows(v, sh, lane);
+        T::template inv_rows<UNI_INV_FUSED>(v, typename T::LanePtrs{nullptr, nullptr, nullptr}, 32 * h);
+        T::sts_rows(v, sh, lane);  // this lane's own slots; the partner warp reads them after the barrier
+        pair_sync(pair);
+        // join the halves: last inverse level + scale, canonical; this warp's 16 register rows of BOTH halves
+        uint32_t* zt = z + tile * G::WORDS;
+#pragma unroll
+        for (uint32_t k = 0; k < HR; k++) {
+            const uint32_t r = HR * h + k, o = T::swz(T::row_off(lane, r));
+            uint32_t a = B[o], b = B[G::HALF + o];
+            T::template split_inv<UNI_INV_FUSED>(a, b);
+            zt[lane + 32 * r] = a;
+            zt[G::HALF + lane + 32 * r] = b;
+        }
+        fence_proxy_async();
+        pair_sync(pair);  // B is free
+        if (more && issuer) issue(y, B, bar_b, tile + stride);
+    }
+}
+
 // Single transform for n = 2048 on the split tile (qt_ntt_forward / qt_ntt_inverse of qTESLA-p-III), in
 // place, NTT domain in bit-reversed order.  Two one-polynomial buffers per warp alternate between staging
 // of the next tile and scratch of the current one, as in k_ntt_tma.
@@ -416,7 +572,7 @@ k_ntt_split(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     extern __shared__ uint4 smem_raw[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
-    constexpr int NW = G::WARPS;
+    const int NW = (int)(blockDim.x >> 5);  // <= SplitShape::WARPS
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf0 = s_stage + warp * 2 * G::WORDS;
@@ -517,7 +673,7 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
     extern __shared__ uint4 smem_raw[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
-    constexpr int NW = TmaCfg<SET>::WARPS;
+    const int NW = (int)(blockDim.x >> 5);  // <= TmaCfg<SET>::WARPS; small batches are launched with fewer warps (less shared memory: the next launch's CTA fits beside this one)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // One y buffer per warp, refilled as soon as the inverse has left it (measured: requesting the next y a
@@ -723,7 +879,7 @@ k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     extern __shared__ uint4 smem_raw[];
     TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
-    constexpr int NW = TmaCfg<SET>::WARPS;
+    const int NW = (int)(blockDim.x >> 5);  // <= TmaCfg<SET>::WARPS; small batches are launched with fewer warps (less shared memory: the next launch's CTA fits beside this one)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* buf0 = s_stage + warp * 2 * G::WORDS;

@@ -501,10 +501,12 @@ template <int SET, int RING> struct Nuss {
 
 #if defined(__CUDACC__)
 
-template <int SET, int RING, bool REC = false>
+// LIFT (ring 2^32-1 only): QT_RING_2P32M1_LIFT_Q — centred Z_q operands in, signed lift reduced mod q out
+template <int SET, int RING, bool REC = false, bool LIFT = false>
 __global__ void __launch_bounds__(NussCfg<SET>::THREADS)
-k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, uint32_t lift) {
+k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
     static_assert(!REC || RING == 1, "recursive row products exist for Z_q only");
+    static_assert(!LIFT || RING == 0, "the lift belongs to the ring 2^32-1");
     using K = NussCfg<SET>;
     using NU = Nuss<SET, RING>;
     extern __shared__ uint4 nuss_smem_raw[];
@@ -520,7 +522,7 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, ui
             const uint32_t per = K::THREADS / K::P, p = tid / per;
             if (p < np)
                 NU::load(tid % per, per, x + (p0 + p) * K::N, y + (p0 + p) * K::N, smem + p * K::POLY_WORDS,
-                         smem + p * K::POLY_WORDS + K::X_WORDS, lift != 0);
+                         smem + p * K::POLY_WORDS + K::X_WORDS, LIFT);
         }
         __syncthreads();
         // forward stages: P polys x 2 operands x m row butterflies per stage, one warp each
@@ -563,7 +565,7 @@ k_nussbaumer(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, ui
         }
         {
             const uint32_t per = K::THREADS / K::P, p = tid / per;
-            if (p < np) NU::store(tid % per, per, smem + p * K::POLY_WORDS, z + (p0 + p) * K::N, lift != 0);
+            if (p < np) NU::store(tid % per, per, smem + p * K::POLY_WORDS, z + (p0 + p) * K::N, LIFT);
         }
         __syncthreads();
     }
@@ -744,9 +746,13 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
     }
 };
 
-template <int SET, int RING, int MODE = 0>
+#ifndef QT_NUSS_PREFETCH
+#define QT_NUSS_PREFETCH 1
+#endif
+template <int SET, int RING, int MODE = 0, bool LIFT = false>
 __global__ void __launch_bounds__(NussWarp<SET, RING, MODE>::WARPS * 32)
-k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, uint32_t lift) {
+k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    static_assert(!LIFT || RING == 0, "the lift belongs to the ring 2^32-1");
     using W = NussWarp<SET, RING, MODE>;
     using K = NussCfg<SET>;
     using O = typename W::O;
@@ -761,6 +767,12 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
     for (size_t p = (size_t)warp * gridDim.x + blockIdx.x; p < batch; p += (size_t)gridDim.x * W::WARPS) {  // SM-interleaved
         const uint32_t* gx = x + p * K::N;
         const uint32_t* gy = y + p * K::N;
+#if QT_NUSS_PREFETCH
+        if (p + (size_t)gridDim.x * W::WARPS < batch) {  // the next polynomial of this warp: its lines towards L2 now
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gx + (size_t)gridDim.x * W::WARPS * K::N + K::M * lane));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + (size_t)gridDim.x * W::WARPS * K::N + K::M * lane));
+        }
+#endif
         uint32_t v[W::ROWS];
 #pragma unroll 1
         for (int op = 0; op < 2; op++) {
@@ -770,7 +782,7 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
                 const uint4 u = g[c];
                 v[4 * c] = u.x; v[4 * c + 1] = u.y; v[4 * c + 2] = u.z; v[4 * c + 3] = u.w;
             }
-            if (RING == 0 && lift) {  // QT_RING_2P32M1_LIFT_Q: centred representatives of the Z_q operands
+            if (LIFT) {  // QT_RING_2P32M1_LIFT_Q: centred representatives of the Z_q operands
 #pragma unroll
                 for (uint32_t i = 0; i < K::M; i++) v[i] = NussOps<SET, 0>::lift_in(v[i]);
             }
@@ -813,11 +825,278 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
                 uint32_t r = (lane == 0) ? O::sub(v[i], up) : O::add(v[i], up);
                 if (W::LAZYQ) r = T::scanon(T::smul_shoup(r, TwPair{1u, T::C::MU32}));  // any |r| < 2^31 -> [0, q)
                 else if (RING == 1) r = T::csub(T::mul_shoup(r, rfix), T::Q);
-                else if (lift) r = NussOps<SET, 0>::lift_out(r);
+                else if (LIFT) r = NussOps<SET, 0>::lift_out(r);
                 o[k] = r;
             }
             gz[c] = make_uint4(o[0], o[1], o[2], o[3]);
         }
+    }
+}
+
+// ---- block-pass warp kernel (m = 32: n = 1024, 2048) --------------------------------------------------------------
+// One WARP per polynomial, like k_nussbaumer_warp, but the 2m = 64 rows are processed as two BLOCKS of 32: every forward
+// stage j < log2 m and every inverse stage j < log2 m pairs rows inside one block (rows m..2m-1 start as copies of rows
+// 0..m-1, NTT.cu:187-191, so the first stage is the copy itself), only the last inverse stage and the recombination join
+// block 0 with block 1.  Per block: load, forward stages in registers (rotation = warp shuffles), rows to shared
+// memory, row products (lane = row, all 32 lanes busy), rows back, inverse stages; block 0's result is parked in the
+// warp's own shared-memory slots while block 1 runs.  What this buys over the whole-polynomial warp kernel:
+//   * 32 * (r/32) row registers live instead of 64 * (r/32): n = 2048 (r = 64: two coefficients per lane) fits a warp at
+//     all — it used to run on the shared-memory kernel k_nussbaumer with one thread per row and CTA-wide barriers;
+//   * Z_q: block 1 is block 0's transform of the TWISTED rows (row i rotated by w^(i r/m) first: the standard split of a
+//     length-2m transform into the even and the odd outputs), so the SAME stage code serves both blocks in a rolled loop —
+//     half the straight-line code of the stage phases (the instruction-fetch stall of the whole-polynomial kernel).
+//     The ring 2^32-1 keeps the reference's own rotation amounts and operation order (two compile-time copies), because
+//     there the representation of zero depends on it.
+template <int SET, int RING, int MODE = 0, bool LIFT = false> struct NussBlk {
+    using K = NussCfg<SET>;
+    using T = Tile<SET>;
+    using W = NussWarp<SET, RING, MODE>;
+    using O = typename W::O;
+    static constexpr uint32_t M = K::M, R = K::R, LOGM = K::LOGM, EPL = R / 32, Q = K::Q, UNIT = K::ROT_UNIT;
+    static_assert(M == 32 && (EPL == 1 || EPL == 2), "block-pass kernel: 32 rows per block, 32 or 64 columns");
+    static constexpr bool LAZYQ = W::LAZYQ, F64 = W::F64, REC = W::REC;
+    static_assert(R == 32 || (!LAZYQ && !F64), "64-column rows exist for the 30-bit modulus only");
+    static_assert(R == 32 || RING == 0 || REC, "64-column Z_q rows: recursive row products");
+    static constexpr bool TWIST = RING == 1;  // block 1 = twisted block 0 (exact in Z_q; see above)
+    static constexpr uint32_t RS = R + 1;                 // row stride: conflict-free along a row and down a column
+    static constexpr uint32_t BLK_WORDS = M * RS;
+    static constexpr uint32_t WARP_WORDS = 3 * BLK_WORDS;  // X rows | Y rows | parked result of block 0
+#ifndef QT_NUSS_BLK_WARPS
+#define QT_NUSS_BLK_WARPS 16
+#endif
+#ifndef QT_NUSS_BLK_WARPS_F64
+#define QT_NUSS_BLK_WARPS_F64 12
+#endif
+    // registers: the three-limb ring products and the FP64 rows want ~170 (12 warps), the recursive rows up to 255 (8 warps)
+    static constexpr uint32_t WARPS = R == 64 ? 8 : ((F64 || RING == 0) ? QT_NUSS_BLK_WARPS_F64 : (REC ? 8 : QT_NUSS_BLK_WARPS));
+    static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_WORDS * sizeof(uint32_t);
+
+    struct Row { uint32_t c[EPL]; };  // coefficients lane + 32 e of one row
+
+    // row * w^s, s in [0, r): coefficient a takes (a - s) mod r, negated on wrap-around (NTT.cu:210-215)
+    static __device__ __forceinline__ Row rot_fwd(Row t, uint32_t s, uint32_t lane) {
+        const int d = (int)lane - (int)s;
+        Row o;
+        if (EPL == 1) {
+            const uint32_t src = __shfl_sync(0xffffffffu, t.c[0], d & 31);
+            o.c[0] = d >= 0 ? src : O::neg(src);
+        } else {
+            const uint32_t a0 = __shfl_sync(0xffffffffu, t.c[0], d & 31), a1 = __shfl_sync(0xffffffffu, t.c[EPL - 1], d & 31);
+            const bool sw = (d >> 5) & 1;  // floor(d / 32) odd: the source sits in the other half
+            const uint32_t r0 = sw ? a1 : a0, r1 = sw ? a0 : a1;
+            o.c[0] = d >= 0 ? r0 : O::neg(r0);
+            o.c[EPL - 1] = d >= -32 ? r1 : O::neg(r1);
+        }
+        return o;
+    }
+    // row * w^-s: coefficient a takes (a + s) mod r, negated on wrap-around (NTT.cu:262-267)
+    static __device__ __forceinline__ Row rot_inv(Row t, uint32_t s, uint32_t lane) {
+        const uint32_t d = lane + s;
+        Row o;
+        if (EPL == 1) {
+            const uint32_t src = __shfl_sync(0xffffffffu, t.c[0], d & 31);
+            o.c[0] = d < 32 ? src : O::neg(src);
+        } else {
+            const uint32_t a0 = __shfl_sync(0xffffffffu, t.c[0], d & 31), a1 = __shfl_sync(0xffffffffu, t.c[EPL - 1], d & 31);
+            const bool sw = (d >> 5) & 1;
+            const uint32_t r0 = sw ? a1 : a0, r1 = sw ? a0 : a1;
+            o.c[0] = d < 64 ? r0 : O::neg(r0);
+            o.c[EPL - 1] = d < 32 ? r1 : O::neg(r1);
+        }
+        return o;
+    }
+    // rotation exponent of stage j, LOCAL group i (of 2^(LOGM-1-j)) of block H:  rot(i + H 2^(LOGM-1-j), j) of the
+    // whole-polynomial numbering = ((brev(i) + H) << j) * UNIT  (the block bit is the top bit of the group index)
+    static __host__ __device__ constexpr uint32_t rot(uint32_t i, uint32_t j, uint32_t H) {
+        return ((c_bitrev(i, LOGM - j) + H) << j) * UNIT;
+    }
+
+    template <uint32_t H> static __device__ __forceinline__ void forward(Row (&v)[M], uint32_t lane) {
+#pragma unroll
+        for (int j = (int)LOGM - 1; j >= 0; j--) {
+#pragma unroll
+            for (uint32_t bf = 0; bf < M / 2; bf++) {
+                const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+                const uint32_t I = (i << (j + 1)) + t, L = I + (1u << j), sr = rot(i, (uint32_t)j, H);
+                Row tv = v[L];
+                if (sr != 0) tv = rot_fwd(tv, sr, lane);
+#pragma unroll
+                for (uint32_t e = 0; e < EPL; e++) {
+                    const uint32_t vi = v[I].c[e];
+                    v[L].c[e] = O::sub(vi, tv.c[e]);
+                    v[I].c[e] = O::add(vi, tv.c[e]);
+                }
+            }
+        }
+    }
+    template <uint32_t H> static __device__ __forceinline__ void inverse(Row (&z)[M], uint32_t lane) {
+#pragma unroll
+        for (uint32_t j = 0; j < LOGM; j++) {
+#pragma unroll
+            for (uint32_t bf = 0; bf < M / 2; bf++) {
+                const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+                const uint32_t A = (i << (j + 1)) + t, B = A + (1u << j), sr = rot(i, j, H);
+                Row tv;
+#pragma unroll
+                for (uint32_t e = 0; e < EPL; e++) {
+                    const uint32_t za = z[A].c[e], zb = z[B].c[e];
+                    tv.c[e] = O::half(O::sub(za, zb));
+                    z[A].c[e] = O::half(O::add(za, zb));
+                }
+                if (sr != 0) tv = rot_inv(tv, sr, lane);
+                z[B] = tv;
+            }
+        }
+    }
+
+    // one row product, rows where they lie in shared memory (z overwrites x)
+    static __device__ __forceinline__ void product_row(uint32_t* xr, uint32_t* yr) {
+        if constexpr (R == 32) W::product_row(xr, yr);
+        else if constexpr (RING == 0) Nuss<SET, 0>::product(xr, yr);
+        else Nuss<SET, 1>::product_recursive(xr, yr);
+    }
+
+    // everything of block H up to its inverse stages; result in v
+    template <uint32_t H> static __device__ __forceinline__ void block(Row (&v)[M], const uint32_t* gx, const uint32_t* gy,
+                                                                     uint32_t* sx, uint32_t* sy, uint32_t lane, bool twist) {
+#pragma unroll 1
+        for (int op = 0; op < 2; op++) {
+#pragma unroll
+            for (uint32_t e = 0; e < EPL; e++) {
+                const uint4* g = reinterpret_cast<const uint4*>((op ? gy : gx) + M * (lane + 32 * e));  // X_i[a] = x[m a + i]
+#pragma unroll
+                for (uint32_t c = 0; c < M / 4; c++) {
+                    const uint4 u = g[c];
+                    v[4 * c].c[e] = u.x; v[4 * c + 1].c[e] = u.y; v[4 * c + 2].c[e] = u.z; v[4 * c + 3].c[e] = u.w;
+                }
+            }
+            if (LIFT) {
+#pragma unroll
+                for (uint32_t i = 0; i < M; i++)
+#pragma unroll
+                    for (uint32_t e = 0; e < EPL; e++) v[i].c[e] = NussOps<SET, 0>::lift_in(v[i].c[e]);
+            }
+            if (W::CENTRE_X) {
+                const uint32_t thr = op ? 0xFFFFFFFFu : T::Q / 2;  // x only
+#pragma unroll
+                for (uint32_t i = 0; i < M; i++) v[i].c[0] -= (v[i].c[0] > thr) ? T::Q : 0u;
+            }
+            if (TWIST && twist) {  // block 1: row i * w^(i r/m), then block 0's stage code
+#pragma unroll
+                for (uint32_t i = 1; i < M; i++) v[i] = rot_fwd(v[i], i * UNIT, lane);
+            }
+            forward<H>(v, lane);
+            if constexpr (F64) {
+                // FP64 row products take operands in [-q/2, 3q/2); x also takes 2^-(LOGM+1), the halvings of the inverse stages
+                const TwPair one{1u, T::C::MU32}, halves = tw_signed_c(c_powmod((T::Q + 1) / 2, LOGM + 1, T::Q), T::Q);
+                const TwPair sw{op ? one.w : halves.w, op ? one.ws : halves.ws};
+#pragma unroll
+                for (uint32_t i = 0; i < M; i++) v[i].c[0] = T::smul_shoup(v[i].c[0], sw);
+            }
+            uint32_t* s = op ? sy : sx;
+#pragma unroll
+            for (uint32_t i = 0; i < M; i++)
+#pragma unroll
+                for (uint32_t e = 0; e < EPL; e++) s[i * RS + lane + 32 * e] = v[i].c[e];
+        }
+        __syncwarp();
+        product_row(sx + lane * RS, sy + lane * RS);
+        __syncwarp();
+#pragma unroll
+        for (uint32_t i = 0; i < M; i++)
+#pragma unroll
+            for (uint32_t e = 0; e < EPL; e++) v[i].c[e] = sx[i * RS + lane + 32 * e];
+        __syncwarp();
+        inverse<H>(v, lane);
+        if (TWIST && twist) {
+#pragma unroll
+            for (uint32_t i = 1; i < M; i++) v[i] = rot_inv(v[i], i * UNIT, lane);
+        }
+    }
+};
+
+template <int SET, int RING, int MODE = 0, bool LIFT = false>
+__global__ void __launch_bounds__(NussBlk<SET, RING, MODE, LIFT>::WARPS * 32)
+k_nussbaumer_blk(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
+    using NB = NussBlk<SET, RING, MODE, LIFT>;
+    using K = NussCfg<SET>;
+    using O = typename NB::O;
+    using T = Tile<SET>;
+    using Row = typename NB::Row;
+    static_assert(!LIFT || RING == 0, "the lift belongs to the ring 2^32-1");
+    constexpr uint32_t M = NB::M, R = NB::R, EPL = NB::EPL, RS = NB::RS;
+    extern __shared__ uint4 nuss_smem_raw[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* sx = reinterpret_cast<uint32_t*>(nuss_smem_raw) + warp * NB::WARP_WORDS;
+    uint32_t* sy = sx + NB::BLK_WORDS;
+    uint32_t* sp = sy + NB::BLK_WORDS;
+    // 2^32 mod q with its Shoup companion: removes the Montgomery factor of the canonical 32-column row products
+    const TwPair rfix{T::C::R_MODQ, (uint32_t)(((uint64_t)T::C::R_MODQ << 32) / T::Q)};
+    const size_t stride = (size_t)gridDim.x * NB::WARPS;
+    for (size_t p = (size_t)warp * gridDim.x + blockIdx.x; p < batch; p += stride) {  // SM-interleaved
+        const uint32_t* gx = x + p * K::N;
+        const uint32_t* gy = y + p * K::N;
+        if (p + stride < batch) {  // next polynomial of this warp: its lines towards L2 while this one is computed
+#pragma unroll
+            for (uint32_t e = 0; e < EPL; e++) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(gx + stride * K::N + M * (lane + 32 * e)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + stride * K::N + M * (lane + 32 * e)));
+            }
+        }
+        Row v[M];
+        if constexpr (NB::TWIST) {
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; h++) {  // one copy of the stage code for both blocks
+                NB::template block<0>(v, gx, gy, sx, sy, lane, h != 0);
+                if (h == 0) {
+#pragma unroll
+                    for (uint32_t i = 0; i < M; i++)
+#pragma unroll
+                        for (uint32_t e = 0; e < EPL; e++) sp[i * RS + lane + 32 * e] = v[i].c[e];  // parked in this lane's own slots
+                }
+            }
+        } else {
+            NB::template block<0>(v, gx, gy, sx, sy, lane, false);
+#pragma unroll
+            for (uint32_t i = 0; i < M; i++)
+#pragma unroll
+                for (uint32_t e = 0; e < EPL; e++) sp[i * RS + lane + 32 * e] = v[i].c[e];
+            NB::template block<1>(v, gx, gy, sx, sy, lane, false);
+        }
+        // last inverse stage (rows i and m+i, no rotation, NTT.cu:241-269 with j = log2 m) and the recombination
+        // z[m a + i] = Z_i[a] + Z_{m+i}[a-1], a = 0 wraps with a sign (NTT.cu:271-276)
+#pragma unroll
+        for (uint32_t c = 0; c < M / 4; c++) {
+            uint32_t o[EPL][4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t i = 4 * c + k;
+                Row za, zb, up;
+#pragma unroll
+                for (uint32_t e = 0; e < EPL; e++) {
+                    const uint32_t a = sp[i * RS + lane + 32 * e], b = v[i].c[e];
+                    zb.c[e] = O::half(O::sub(a, b));
+                    za.c[e] = O::half(O::add(a, b));
+                }
+                // up[a] = Z_{m+i}[a - 1]
+                const uint32_t u0 = __shfl_sync(0xffffffffu, zb.c[0], (lane - 1) & 31u);
+                const uint32_t u1 = EPL == 2 ? __shfl_sync(0xffffffffu, zb.c[EPL - 1], (lane - 1) & 31u) : u0;
+                up.c[0] = (EPL == 2 && lane == 0) ? u1 : u0;  // a = 0 takes coefficient r - 1 (subtracted)
+                if (EPL == 2) up.c[EPL - 1] = lane == 0 ? u0 : u1;  // a = 32 takes coefficient 31
+#pragma unroll
+                for (uint32_t e = 0; e < EPL; e++) {
+                    uint32_t r = (e == 0 && lane == 0) ? O::sub(za.c[e], up.c[e]) : O::add(za.c[e], up.c[e]);
+                    if (NB::LAZYQ) r = T::scanon(T::smul_shoup(r, TwPair{1u, T::C::MU32}));  // any |r| < 2^31 -> [0, q)
+                    else if (RING == 1 && R == 32) r = T::csub(T::mul_shoup(r, rfix), T::Q);
+                    else if (LIFT) r = NussOps<SET, 0>::lift_out(r);
+                    o[e][k] = r;
+                }
+            }
+#pragma unroll
+            for (uint32_t e = 0; e < EPL; e++)
+                reinterpret_cast<uint4*>(z + p * K::N + M * (lane + 32 * e))[c] = make_uint4(o[e][0], o[e][1], o[e][2], o[e][3]);
+        }
+        __syncwarp();  // the parked slots and the row buffers are rewritten by the next polynomial
     }
 }
 
@@ -829,7 +1108,18 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
 #ifndef QT_NUSS_AUTO_F64
 #define QT_NUSS_AUTO_F64 1
 #endif
-enum : int { NUSS_AUTO = 0, NUSS_SCHOOLBOOK = 1, NUSS_RECURSIVE = 2, NUSS_FP64 = 3 };
+enum : int { NUSS_AUTO = 0, NUSS_SCHOOLBOOK = 1, NUSS_RECURSIVE = 2, NUSS_FP64 = 3,
+             NUSS_WHOLE = 16 };  // flag: the whole-polynomial kernels of round 1 instead of the block-pass kernel (A/B)
+#ifndef QT_NUSS_BLK
+#define QT_NUSS_BLK 1  // the block-pass warp kernel serves the m = 32 sets (n = 1024, 2048)
+#endif
+// measured (run r02f): n = 2048 15.6 vs 12.2 M polymul/s (Z_q, recursive rows) and 6.9 vs 5.8 (ring 2^32-1) against the shared-memory
+// kernel; n = 1024 it LOSES to the whole-polynomial warp kernel (FP64 rows 78.8 vs 86.1, ring 41.0 vs 48.7: the second pass
+// re-reads the operands and the twist costs 3 x 31 extra rotations), so it serves the 64-column split only
+#ifndef QT_NUSS_BLK_ALL
+#define QT_NUSS_BLK_ALL 0
+#endif
+template <int SET> constexpr bool nuss_has_blk() { return QT_NUSS_BLK && NussCfg<SET>::M == 32 && (QT_NUSS_BLK_ALL || NussCfg<SET>::R == 64); }
 template <int SET> constexpr bool nuss_has_f64() { return NussCfg<SET>::R == 32 && NussRowF64<SET>::OK; }
 
 template <class Kern> int nuss_prepare(Kern k, int threads, size_t smem, int* occ_min) {
@@ -845,10 +1135,23 @@ template <class Kern> int nuss_prepare(Kern k, int threads, size_t smem, int* oc
 template <int SET> int nuss_setup(int num_sms, int* grid) {
     using K = NussCfg<SET>;
     int occ = 64, rc = 0;
+    if constexpr (nuss_has_blk<SET>()) {  // grid = #SMs (one CTA each); the occupancy of these is not part of `grid`
+        int o1 = 64;
+        if ((rc = nuss_prepare(k_nussbaumer_blk<SET, 0, 0>, NussBlk<SET, 0, 0>::WARPS * 32, NussBlk<SET, 0, 0>::SMEM_BYTES, &o1))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_blk<SET, 0, 0, true>, NussBlk<SET, 0, 0, true>::WARPS * 32, NussBlk<SET, 0, 0, true>::SMEM_BYTES, &o1))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_blk<SET, 1, 1>, NussBlk<SET, 1, 1>::WARPS * 32, NussBlk<SET, 1, 1>::SMEM_BYTES, &o1))) return rc;
+        if constexpr (K::R == 32) {
+            if ((rc = nuss_prepare(k_nussbaumer_blk<SET, 1, 0>, NussBlk<SET, 1, 0>::WARPS * 32, NussBlk<SET, 1, 0>::SMEM_BYTES, &o1))) return rc;
+            if constexpr (nuss_has_f64<SET>())
+                if ((rc = nuss_prepare(k_nussbaumer_blk<SET, 1, 2>, NussBlk<SET, 1, 2>::WARPS * 32, NussBlk<SET, 1, 2>::SMEM_BYTES, &o1))) return rc;
+        }
+        if (o1 < 1) return -4;
+    }
     if constexpr (K::R == 32) {  // warp-resident kernels
         using W = NussWarp<SET, 0>;
         using WR = NussWarp<SET, 1, 1>;
         if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 0, 0>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 0, 0, true>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
         if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 0>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
         if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 1>, WR::WARPS * 32, WR::SMEM_BYTES, &occ))) return rc;
         if constexpr (nuss_has_f64<SET>()) {
@@ -857,6 +1160,7 @@ template <int SET> int nuss_setup(int num_sms, int* grid) {
         }
     } else {
         if ((rc = nuss_prepare(k_nussbaumer<SET, 0, false>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer<SET, 0, false, true>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
         if ((rc = nuss_prepare(k_nussbaumer<SET, 1, false>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
         if ((rc = nuss_prepare(k_nussbaumer<SET, 1, true>, K::THREADS, K::SMEM_BYTES, &occ))) return rc;
     }
@@ -866,30 +1170,55 @@ template <int SET> int nuss_setup(int num_sms, int* grid) {
 
 template <int SET>
 int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, int ring, int variant,
-                cudaStream_t s) {
+                cudaStream_t s, int grid_occ = 1) {
     using K = NussCfg<SET>;
+    const bool whole = (variant & NUSS_WHOLE) != 0;
+    variant &= ~NUSS_WHOLE;
     const uint32_t lift = ring == 2 ? 1u : 0u;  // QT_RING_2P32M1_LIFT_Q: the ring 2^32-1 kernels with the lift epilogue
     if (ring == 2) ring = 0;
     const bool f64 = ring == 1 && nuss_has_f64<SET>() && (variant == NUSS_FP64 || (variant == NUSS_AUTO && QT_NUSS_AUTO_F64));
     const bool rec = ring == 1 && !f64 && (variant == NUSS_RECURSIVE || (variant == NUSS_AUTO && QT_NUSS_AUTO_RECURSIVE));
     if (variant == NUSS_FP64 && ring == 1 && !nuss_has_f64<SET>()) return -4;  // QT_ERR_UNSUPPORTED
+    if constexpr (nuss_has_blk<SET>()) {
+        // block-pass warp kernel; 64-column Z_q rows exist in recursive form only (schoolbook on request: whole-polynomial kernel)
+        const bool blk_ok = !whole && !(K::R == 64 && ring == 1 && !rec) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15) == 0;
+        if (blk_ok) {
+            const int sms = max_grid / (grid_occ < 1 ? 1 : grid_occ);
+            const int g = (int)(batch < (size_t)sms ? batch : (size_t)sms);
+#define QT_BLK_LAUNCH(RING_, MODE_, LIFT_)                                                                         \
+    k_nussbaumer_blk<SET, RING_, MODE_, LIFT_><<<g, NussBlk<SET, RING_, MODE_, LIFT_>::WARPS * 32,                 \
+                                                 NussBlk<SET, RING_, MODE_, LIFT_>::SMEM_BYTES, s>>>(x, y, z, batch)
+            if (ring == 0 && lift) QT_BLK_LAUNCH(0, 0, true);
+            else if (ring == 0) QT_BLK_LAUNCH(0, 0, false);
+            else if (rec) QT_BLK_LAUNCH(1, 1, false);
+            else if constexpr (K::R == 32) {
+                if (f64) {
+                    if constexpr (nuss_has_f64<SET>()) QT_BLK_LAUNCH(1, 2, false);
+                } else QT_BLK_LAUNCH(1, 0, false);
+            }
+#undef QT_BLK_LAUNCH
+            return (int)cudaGetLastError();
+        }
+    }
     if constexpr (K::R == 32) {
         if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15) != 0) return -2;  // 128-bit accesses
         using W = NussWarp<SET, 0>;
         const int g = (int)(batch < (size_t)max_grid ? batch : (size_t)max_grid);  // small batches spread over all SMs
-        if (ring == 0) k_nussbaumer_warp<SET, 0, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch, lift);
+        if (ring == 0 && lift) k_nussbaumer_warp<SET, 0, 0, true><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        else if (ring == 0) k_nussbaumer_warp<SET, 0, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
         else if (f64) {
             if constexpr (nuss_has_f64<SET>())
-                k_nussbaumer_warp<SET, 1, 2><<<g, NussWarp<SET, 1, 2>::WARPS * 32, NussWarp<SET, 1, 2>::SMEM_BYTES, s>>>(x, y, z, batch, lift);
-        } else if (rec) k_nussbaumer_warp<SET, 1, 1><<<g, NussWarp<SET, 1, 1>::WARPS * 32, NussWarp<SET, 1, 1>::SMEM_BYTES, s>>>(x, y, z, batch, lift);
-        else k_nussbaumer_warp<SET, 1, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch, lift);
+                k_nussbaumer_warp<SET, 1, 2><<<g, NussWarp<SET, 1, 2>::WARPS * 32, NussWarp<SET, 1, 2>::SMEM_BYTES, s>>>(x, y, z, batch);
+        } else if (rec) k_nussbaumer_warp<SET, 1, 1><<<g, NussWarp<SET, 1, 1>::WARPS * 32, NussWarp<SET, 1, 1>::SMEM_BYTES, s>>>(x, y, z, batch);
+        else k_nussbaumer_warp<SET, 1, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
         return (int)cudaGetLastError();
     } else {
         const size_t groups = (batch + K::P - 1) / K::P;
         const int grid = (int)(groups < (size_t)max_grid ? groups : (size_t)max_grid);
-        if (ring == 0) k_nussbaumer<SET, 0, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch, lift);
-        else if (rec) k_nussbaumer<SET, 1, true><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch, lift);
-        else k_nussbaumer<SET, 1, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch, lift);
+        if (ring == 0 && lift) k_nussbaumer<SET, 0, false, true><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+        else if (ring == 0) k_nussbaumer<SET, 0, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+        else if (rec) k_nussbaumer<SET, 1, true><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
+        else k_nussbaumer<SET, 1, false><<<grid, K::THREADS, K::SMEM_BYTES, s>>>(x, y, z, batch);
         return (int)cudaGetLastError();
     }
 }

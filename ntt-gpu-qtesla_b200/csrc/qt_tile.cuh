@@ -30,6 +30,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <utility>
 
 #include "qt_params.h"
 #include "qt_tables.h"
@@ -76,6 +77,113 @@ QT_HD int32_t mulhi32s(uint32_t a, uint32_t b) {  // signed high word of two two
 QT_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 struct alignas(16) U4 { uint32_t x, y, z, w; };  // 128-bit shared-memory access unit
+
+// ---- static range plan of the Harvey path when the modulus leaves head-room --------------------------------------
+// Harvey's butterfly keeps everything in [0, 4q) by one conditional subtraction per butterfly (2 of its 4 ALU
+// instructions).  For qTESLA-p-I 2^32 / q = 12.5, so a value may grow to 12 q before it has to be touched, and WHICH
+// registers grow is a function of the register index only: the x input of a Cooley-Tukey butterfly gains 2q per
+// level, the y input is reset to [0, 2q) by its Shoup multiplication; in the Gentleman-Sande inverse the sum output
+// adds the two bounds and the product output is reset.  The plan below runs that bookkeeping at COMPILE TIME over the
+// unrolled butterfly network of one thread and records where a conditional subtraction is really needed (and by how
+// many q): 308 instead of 576 per product and thread for n = 1024.  Bounds are in units of q ("b" means value < b q);
+// at the shared-memory transpositions the worst register's bound is taken for all (a thread's registers there come
+// from different registers of 32 other threads).
+template <uint32_t E, uint32_t LB1, uint32_t LB2, uint32_t CAP> struct HarveyPlan {
+    struct P {
+        uint8_t fr[LB1][E / 2];     // forward, rows levels: csub modulus (x q) applied to x before butterfly i, 0 = none
+        uint8_t fc[LB2][E / 2];     // forward, cols levels
+        uint8_t fout[E];            // bounds of the forward output
+        uint8_t pwa[E][3], pwb[E][3];  // pointwise product of two forward outputs: csub chains of either operand
+        uint8_t cf[E][4];           // forward output -> canonical: csub chain down to 1
+        uint8_t ic[LB2][E / 2][2];  // inverse, cols levels: csub modulus of a / of b before the butterfly
+        uint8_t ick[LB2][E / 2];    // ... bound of a when the difference b - a + K q is formed
+        uint8_t ir[LB1][E / 2][2];  // inverse, rows levels
+        uint8_t irk[LB1][E / 2];    // ... bound of b (difference a - b + K q)
+        uint8_t rows_out, icols_out, ok;
+    };
+    static QT_CHD uint32_t halve(uint32_t b) { return (b + 1) / 2; }  // csub(v, m q) with m = ceil(b / 2): [0, b q) -> [0, m q)
+    static QT_CHD P make() {
+        P p{};
+        p.ok = 1;
+        uint32_t b[E] = {};
+        for (uint32_t r = 0; r < E; r++) b[r] = 1;  // canonical input
+        for (uint32_t l = 0; l < LB1; l++) {
+            const uint32_t half = E >> (l + 1);
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t x = 2 * (i / half) * half + i % half, y = x + half;
+                if (b[x] + 2 > CAP) { p.fr[l][i] = (uint8_t)halve(b[x]); b[x] = halve(b[x]); }
+                if (b[x] + 2 > CAP) p.ok = 0;
+                b[x] += 2; b[y] = b[x];
+            }
+        }
+        uint32_t u = 0;
+        for (uint32_t r = 0; r < E; r++) u = b[r] > u ? b[r] : u;
+        p.rows_out = (uint8_t)u;
+        for (uint32_t r = 0; r < E; r++) b[r] = u;
+        for (uint32_t k = 0; k < LB2; k++) {
+            const uint32_t half = (E >> 1) >> k;
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t x = 2 * (i / half) * half + i % half, y = x + half;
+                if (b[x] + 2 > CAP) { p.fc[k][i] = (uint8_t)halve(b[x]); b[x] = halve(b[x]); }
+                if (b[x] + 2 > CAP) p.ok = 0;
+                b[x] += 2; b[y] = b[x];
+            }
+        }
+        for (uint32_t r = 0; r < E; r++) {
+            p.fout[r] = (uint8_t)b[r];
+            uint32_t ba = b[r], bb = b[r], na = 0, nb = 0;  // a b < q 2^32  <=  ba bb <= CAP
+            while (ba * bb > CAP) {
+                if (ba >= bb) { ba = halve(ba); if (na < 3) p.pwa[r][na] = (uint8_t)ba; na++; }
+                else { bb = halve(bb); if (nb < 3) p.pwb[r][nb] = (uint8_t)bb; nb++; }
+            }
+            if (na > 3 || nb > 3) p.ok = 0;
+            uint32_t c = b[r], nc = 0;
+            while (c > 1) { c = halve(c); if (nc < 4) p.cf[r][nc] = (uint8_t)c; nc++; }
+            if (nc > 4) p.ok = 0;
+        }
+        for (uint32_t r = 0; r < E; r++) b[r] = 2;  // Montgomery product / canonical NTT-domain input
+        for (uint32_t k = 0; k < LB2; k++) {
+            const uint32_t half = 1u << k;
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t a = 2 * (i / half) * half + i % half, c = a + half;
+                if (b[a] + b[c] > CAP) {
+                    if (b[a] >= b[c]) { p.ic[k][i][0] = (uint8_t)halve(b[a]); b[a] = halve(b[a]); }
+                    else { p.ic[k][i][1] = (uint8_t)halve(b[c]); b[c] = halve(b[c]); }
+                }
+                if (b[a] + b[c] > CAP) {  // second step on the other / the still larger operand
+                    if (b[a] >= b[c] && !p.ic[k][i][0]) { p.ic[k][i][0] = (uint8_t)halve(b[a]); b[a] = halve(b[a]); }
+                    else if (!p.ic[k][i][1]) { p.ic[k][i][1] = (uint8_t)halve(b[c]); b[c] = halve(b[c]); }
+                }
+                if (b[a] + b[c] > CAP) p.ok = 0;
+                p.ick[k][i] = (uint8_t)b[a];
+                b[a] += b[c]; b[c] = 2;
+            }
+        }
+        u = 0;
+        for (uint32_t r = 0; r < E; r++) u = b[r] > u ? b[r] : u;
+        p.icols_out = (uint8_t)u;
+        for (uint32_t r = 0; r < E; r++) b[r] = u;
+        for (uint32_t k = 0; k < LB1; k++) {
+            const uint32_t half = 1u << k;
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t a = 2 * (i / half) * half + i % half, c = a + half;
+                if (b[a] + b[c] > CAP) {
+                    if (b[a] >= b[c]) { p.ir[k][i][0] = (uint8_t)halve(b[a]); b[a] = halve(b[a]); }
+                    else { p.ir[k][i][1] = (uint8_t)halve(b[c]); b[c] = halve(b[c]); }
+                }
+                if (b[a] + b[c] > CAP) {
+                    if (b[a] >= b[c] && !p.ir[k][i][0]) { p.ir[k][i][0] = (uint8_t)halve(b[a]); b[a] = halve(b[a]); }
+                    else if (!p.ir[k][i][1]) { p.ir[k][i][1] = (uint8_t)halve(b[c]); b[c] = halve(b[c]); }
+                }
+                if (b[a] + b[c] > CAP) p.ok = 0;
+                p.irk[k][i] = (uint8_t)b[c];
+                b[a] += b[c]; b[c] = 2;  // (the last level multiplies both outputs: any bound is fine for a Shoup product)
+            }
+        }
+        return p;
+    }
+};
+
 
 // SHIFT_OK = false switches the shift-add form of hi*q off (see ct(); it costs the natural-order inverse
 // kernel 12 % while every other kernel gains or is unaffected).
@@ -179,11 +287,93 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
         b = mul_shoup(d, t_mirror);
     }
 
+    // ---- Harvey path with a static range plan (HarveyPlan above; qTESLA-p-I) ---------------------------------
+    static constexpr bool HLAZY = !LAZY && !C::SPLIT && QCAP >= 8;
+    static_assert(!HLAZY || (LB1 + LOGE == LOGN && PPW == 1), "range plan: written for one polynomial per warp");
+    using HPlan = HarveyPlan<E, LB1, LB2, QCAP>;
+    static_assert(!HLAZY || HPlan::make().ok == 1, "range plan: a value would leave 32 bits");
+    template <uint32_t M_> static QT_HD uint32_t csub_q(uint32_t a) {  // [0, 2 M q) -> [0, M q); M = 0: nothing
+        if constexpr (M_ == 0) return a;
+        else return umin32(a, a - M_ * Q);
+    }
+    template <uint32_t L, uint32_t I> static QT_HD void h_fr(uint32_t (&v)[E], uint32_t ub) {
+        constexpr uint32_t half = E >> (L + 1), g = I / half, X = 2 * g * half + I % half, Y = X + half;
+        constexpr uint32_t m = HPlan::make().fr[L][I];
+        const uint32_t wy = mul_shoup(v[Y], uni_tw<SET, UNI_FWD>(ub + (1u << L) + g)), xx = csub_q<m>(v[X]);
+        v[X] = xx + wy;
+        v[Y] = xx - wy + TWO_Q;
+    }
+    template <uint32_t K, uint32_t I> static QT_HD void h_fc(uint32_t (&v)[E], const TwQuad* tw) {
+        constexpr uint32_t half = (E >> 1) >> K, G = E / (2 * half), g = I / half, X = 2 * g * half + I % half, Y = X + half;
+        constexpr uint32_t m = HPlan::make().fc[K][I];
+        const uint32_t wy = mul_shoup(v[Y], lane_slot(tw, G - G0 + g, BLOCKS)), xx = csub_q<m>(v[X]);
+        v[X] = xx + wy;
+        v[Y] = xx - wy + TWO_Q;
+    }
+    template <uint32_t K, uint32_t I> static QT_HD void h_ic(uint32_t (&v)[E], const TwQuad* tw) {
+        constexpr uint32_t half = 1u << K, G = E / (2 * half), g = I / half, A = 2 * g * half + I % half, B = A + half;
+        constexpr auto pl = HPlan::make();
+        constexpr uint32_t ma = pl.ic[K][I][0], mb = pl.ic[K][I][1], kq = pl.ick[K][I];
+        const uint32_t a = csub_q<ma>(v[A]), b = csub_q<mb>(v[B]);
+        v[A] = a + b;
+        v[B] = mul_shoup(b - a + kq * Q, lane_slot(tw, G - G0 + (G - 1 - g), BLOCKS));
+    }
+    template <int KIND, uint32_t K, uint32_t I> static QT_HD void h_ir(uint32_t (&v)[E], uint32_t ub) {
+        constexpr uint32_t l = LB1 - 1 - K, half = 1u << K, g = I / half, A = 2 * g * half + I % half, B = A + half;
+        constexpr auto pl = HPlan::make();
+        constexpr uint32_t ma = pl.ir[K][I][0], mb = pl.ir[K][I][1], kq = pl.irk[K][I];
+        const uint32_t a = csub_q<ma>(v[A]), b = csub_q<mb>(v[B]);
+        const TwPair t = uni_tw<SET, KIND>(ub + (1u << l) + g);
+        const uint32_t s_ = a + b, d = a - b + kq * Q;
+        if constexpr (l != 0) {
+            v[A] = s_;
+            v[B] = mul_shoup(d, t);
+        } else {  // last level: both outputs are multiplied (K resp. K*zeta^-1), canonical
+            v[A] = csub(mul_shoup(s_, uni_tw<SET, KIND>(0)), Q);
+            v[B] = csub(mul_shoup(d, t), Q);
+        }
+    }
+    template <uint32_t R_> static QT_HD uint32_t h_pw(uint32_t a, uint32_t b) {  // two forward outputs
+        constexpr auto pl = HPlan::make();
+        a = csub_q<pl.pwa[R_][2]>(csub_q<pl.pwa[R_][1]>(csub_q<pl.pwa[R_][0]>(a)));
+        b = csub_q<pl.pwb[R_][2]>(csub_q<pl.pwb[R_][1]>(csub_q<pl.pwb[R_][0]>(b)));
+        return mul_mont(a, b);
+    }
+    template <uint32_t R_> static QT_HD uint32_t h_canon(uint32_t a) {
+        constexpr auto pl = HPlan::make();
+        return csub_q<pl.cf[R_][3]>(csub_q<pl.cf[R_][2]>(csub_q<pl.cf[R_][1]>(csub_q<pl.cf[R_][0]>(a))));
+    }
+    // (compile-time loops: the plan entries must be constant expressions, which loop variables are not)
+    template <uint32_t L, uint32_t... Is> static QT_HD void h_fr_level(uint32_t (&v)[E], uint32_t ub, std::integer_sequence<uint32_t, Is...>) { (h_fr<L, Is>(v, ub), ...); }
+    template <uint32_t... Ls> static QT_HD void h_fr_all(uint32_t (&v)[E], uint32_t ub, std::integer_sequence<uint32_t, Ls...>) { (h_fr_level<Ls>(v, ub, std::make_integer_sequence<uint32_t, E / 2>{}), ...); }
+    template <uint32_t K, uint32_t... Is> static QT_HD void h_fc_level(uint32_t (&v)[E], const TwQuad* tw, std::integer_sequence<uint32_t, Is...>) { (h_fc<K, Is>(v, tw), ...); }
+    template <uint32_t... Ks> static QT_HD void h_fc_all(uint32_t (&v)[E], const TwQuad* tw, std::integer_sequence<uint32_t, Ks...>) { (h_fc_level<Ks>(v, tw, std::make_integer_sequence<uint32_t, E / 2>{}), ...); }
+    template <uint32_t K, uint32_t... Is> static QT_HD void h_ic_level(uint32_t (&v)[E], const TwQuad* tw, std::integer_sequence<uint32_t, Is...>) { (h_ic<K, Is>(v, tw), ...); }
+    template <uint32_t... Ks> static QT_HD void h_ic_all(uint32_t (&v)[E], const TwQuad* tw, std::integer_sequence<uint32_t, Ks...>) { (h_ic_level<Ks>(v, tw, std::make_integer_sequence<uint32_t, E / 2>{}), ...); }
+    template <int KIND, uint32_t K, uint32_t... Is> static QT_HD void h_ir_level(uint32_t (&v)[E], uint32_t ub, std::integer_sequence<uint32_t, Is...>) { (h_ir<KIND, K, Is>(v, ub), ...); }
+    template <int KIND, uint32_t... Ks> static QT_HD void h_ir_all(uint32_t (&v)[E], uint32_t ub, std::integer_sequence<uint32_t, Ks...>) { (h_ir_level<KIND, Ks>(v, ub, std::make_integer_sequence<uint32_t, E / 2>{}), ...); }
+    template <uint32_t... Rs> static QT_HD void h_pw_all(uint32_t (&a)[E], const uint32_t (&b)[E], std::integer_sequence<uint32_t, Rs...>) { ((a[Rs] = h_pw<Rs>(a[Rs], b[Rs])), ...); }
+    template <uint32_t... Rs> static QT_HD void h_canon_all(uint32_t (&v)[E], std::integer_sequence<uint32_t, Rs...>) { ((v[Rs] = h_canon<Rs>(v[Rs])), ...); }
+    template <uint32_t... Cs> static QT_HD void h_pw_stash(uint32_t (&a)[E], const uint32_t* stash, uint32_t lane, std::integer_sequence<uint32_t, Cs...>) {
+        (([&] {
+             const U4 u = *reinterpret_cast<const U4*>(stash + swz(E * lane + 4 * Cs));
+             a[4 * Cs] = h_pw<4 * Cs>(a[4 * Cs], u.x);
+             a[4 * Cs + 1] = h_pw<4 * Cs + 1>(a[4 * Cs + 1], u.y);
+             a[4 * Cs + 2] = h_pw<4 * Cs + 2>(a[4 * Cs + 2], u.z);
+             a[4 * Cs + 3] = h_pw<4 * Cs + 3>(a[4 * Cs + 3], u.w);
+         }()),
+         ...);
+    }
+
     // ---- transforms on one lane's registers ---------------------------------------------------
     // rows layout, forward levels 0..LB1-1 (register distance E/2 .. 1)
     // ub: offset into the uniform tables (split tiles: 32 * half, a run-time value; otherwise 0 and
     // every index is a compile-time constant)
     static QT_HD void fwd_rows(uint32_t (&v)[E], uint32_t ub = 0) {
+        if constexpr (HLAZY) {
+            h_fr_all(v, ub, std::make_integer_sequence<uint32_t, LB1>{});
+            return;
+        }
 #pragma unroll
         for (uint32_t l = 0; l < LB1; l++) {
             const uint32_t half = E >> (l + 1);
@@ -202,6 +392,10 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
 
     // cols layout, forward levels LB1..LOGN-1 (register distance N>>(l+1)); tw = lane_ptrs().fwd
     static QT_HD void fwd_cols(uint32_t (&v)[E], const TwQuad* tw) {
+        if constexpr (HLAZY) {
+            h_fc_all(v, tw, std::make_integer_sequence<uint32_t, LB2>{});
+            return;
+        }
 #pragma unroll
         for (uint32_t k = 0; k < LB2; k++) {
             const uint32_t half = (E >> 1) >> (k + LB1 + LOGE - LOGN);  // N >> (l+1), l = LB1 + k
@@ -222,6 +416,10 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
     //  Harvey: merged Gentleman-Sande; tw = lane_ptrs().inv (the forward table mirrored: zeta[k]^-1 =
     //          -zeta[k'], k' the mirror of k in its level).  Input < 2q.
     static QT_HD void inv_cols(uint32_t (&v)[E], const TwQuad* tw) {
+        if constexpr (HLAZY) {
+            h_ic_all(v, tw, std::make_integer_sequence<uint32_t, LB2>{});
+            return;
+        }
         if (LAZY) {
 #pragma unroll
             for (uint32_t s_ = 0; s_ < LB2; s_++) {
@@ -260,6 +458,10 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
     //          scale table also carries the 2^32 of the pointwise Montgomery product.
     //  Harvey: merged Gentleman-Sande with uniform twiddles, scale folded into the last level.
     template <int KIND> static QT_HD void inv_rows(uint32_t (&v)[E], const LanePtrs& p, uint32_t ub = 0) {
+        if constexpr (HLAZY) {
+            h_ir_all<KIND>(v, ub, std::make_integer_sequence<uint32_t, LB1>{});
+            return;
+        }
         if (LAZY) {
 #pragma unroll
             for (uint32_t k = 0; k < LB1; k++) {
@@ -316,11 +518,19 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
         return LAZY ? smul_mont(a, b) : mul_mont(csub(a, TWO_Q), csub(b, TWO_Q));
     }
     static QT_HD void pointwise_mont(uint32_t (&a)[E], const uint32_t (&b)[E]) {
+        if constexpr (HLAZY) {
+            h_pw_all(a, b, std::make_integer_sequence<uint32_t, E>{});
+            return;
+        }
 #pragma unroll
         for (uint32_t r = 0; r < E; r++) a[r] = pw(a[r], b[r]);
     }
     // same, the second operand read back from a stash written with sts_cols (keeps it out of registers)
     static QT_HD void pointwise_mont_stash(uint32_t (&a)[E], const uint32_t* stash, uint32_t lane) {
+        if constexpr (HLAZY) {
+            h_pw_stash(a, stash, lane, std::make_integer_sequence<uint32_t, E / 4>{});
+            return;
+        }
 #pragma unroll
         for (uint32_t c = 0; c < E / 4; c++) {
             const U4 u = *reinterpret_cast<const U4*>(stash + swz(E * lane + 4 * c));
@@ -332,6 +542,7 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
     }
     // forward output times a canonical NTT-domain operand (qt_polymul_ntt)
     static QT_HD uint32_t pw_canonical(uint32_t a, uint32_t b_canonical) {
+        if constexpr (HLAZY) return mul_mont(a, b_canonical);  // a < QCAP q, b < q: a b < q 2^32 as it is
         return LAZY ? smul_mont(a, b_canonical) : mul_mont(csub(a, TWO_Q), b_canonical);
     }
 
@@ -343,6 +554,10 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
     static constexpr uint64_t KMAX = ((2 + 3 * (uint64_t)LOGN) * Q >> (QS + 1)) + 2;  // |k| bound
     static_assert(!LAZY || ((1ull << (QS - 1)) + KMAX * (Q - (1u << QS)) < Q), "canon_fwd: shift-based quotient");
     static QT_HD void canon_fwd(uint32_t (&v)[E]) {
+        if constexpr (HLAZY) {
+            h_canon_all(v, std::make_integer_sequence<uint32_t, E>{});
+            return;
+        }
 #pragma unroll
         for (uint32_t r = 0; r < E; r++) {
             if (LAZY) {

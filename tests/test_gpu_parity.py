@@ -41,15 +41,16 @@ def rand_pair(q, words, seed):
     return rng.integers(0, q, words, dtype=np.uint32), rng.integers(0, q, words, dtype=np.uint32)
 
 
-# 0 = automatic, 1 = direct coalesced loads, 2 = TMA bulk copies + mbarrier, 3 = n=2048 as two halves
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+# 0 = automatic, 1 = direct coalesced loads, 2 = TMA bulk copies + mbarrier, 3 = n=2048 as two halves (one warp),
+# 4 = n=2048 as two halves by a pair of warps
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("s", ALL_SETS)
 @pytest.mark.parametrize("B", [1, 2, 3, 67, 1000, 5001])
 def test_fused_polymul_equals_oracle(engines, oracle, s, B, variant):
     eng = engines[s]
-    if variant == 3 and s != 3:
+    if variant in (3, 4) and s != 3:
         with pytest.raises(Exception):
-            eng.set_fused_variant(3)   # the split tile exists for n=2048 only
+            eng.set_fused_variant(variant)   # the split tile exists for n=2048 only
         return
     eng.set_fused_variant(variant)
     try:
@@ -69,7 +70,7 @@ def test_fuzz_batches_sets_variants(engines, oracle):
         s = int(rng.integers(0, 4))
         eng = engines[s]
         B = int(special[it % len(special)] if it % 3 == 0 else rng.integers(1, 3000))
-        variant = int(rng.choice([0, 1, 2] + ([3] if s == 3 else [])))
+        variant = int(rng.choice([0, 1, 2] + ([3, 4] if s == 3 else [])))
         eng.set_fused_variant(variant)
         try:
             x, y = rand_pair(eng.q, B * eng.n, 5000 + it)
@@ -97,8 +98,16 @@ def test_fused_variants_agree_at_full_size(engines, s):
     eng.set_fused_variant(2); eng.polymul(x, y, z2)
     eng.set_fused_variant(0); eng.synchronize()
     assert torch.equal(z1, z2)
-    eng.polymul(x, y, z2); eng.synchronize()      # automatic choice (n=2048: the split-tile kernel)
+    eng.polymul(x, y, z2); eng.synchronize()      # automatic choice (n=2048: two warps per polynomial)
     assert torch.equal(z1, z2)
+    if s == 3:
+        for v in (3, 4):                          # both split-tile kernels, full batch and a ragged one
+            eng.set_fused_variant(v)
+            z2.zero_(); eng.polymul(x, y, z2); eng.synchronize()
+            assert torch.equal(z1, z2), v
+            z2.zero_(); eng.polymul(x, y, z2, B - 149); eng.synchronize()
+            assert torch.equal(z1[: (B - 149) * eng.n], z2[: (B - 149) * eng.n]) and not z2[(B - 149) * eng.n:].any(), v
+        eng.set_fused_variant(0)
 
 
 def test_golden_vectors_III(engines, golden):

@@ -26,8 +26,9 @@ for name in args.sets.split(","):
     with torch.cuda.stream(stream):
         eng.fill_uniform(x, 1, 0); eng.fill_uniform(y, 2, 0)
     ref = None
-    for label, ring, nv in (("ring 2^32-1", 0, 0), ("Z_q schoolbook rows", 1, 1), ("Z_q recursive rows", 1, 2),
-                            ("Z_q FP64-pipe rows", 1, 3), ("Z_q automatic", 1, 0)):
+    for label, ring, nv in (("ring 2^32-1", 0, 0), ("ring 2^32-1 [whole]", 0, 16), ("ring lift", 2, 0), ("Z_q schoolbook rows", 1, 1), ("Z_q schoolbook [whole]", 1, 17),
+                            ("Z_q recursive rows", 1, 2), ("Z_q recursive [whole]", 1, 18),
+                            ("Z_q FP64-pipe rows", 1, 3), ("Z_q FP64 [whole]", 1, 19), ("Z_q automatic", 1, 0)):
         try:
             eng.set_nussbaumer_variant(nv)
         except qt.QtError as ex:
@@ -46,5 +47,9 @@ for name in args.sets.split(","):
             h = z.cpu().numpy()
             if ref is None: ref = h
             else: same = "  identical to schoolbook: %s" % bool(np.array_equal(ref, h))
+        elif ring == 0:
+            h = z.cpu().numpy()
+            if nv == 0: ref0 = h
+            else: same = "  identical to block-pass: %s" % bool(np.array_equal(ref0, h))
         print(f"{name:6s} {label:22s}: {r/1e6:8.2f} M polymul/s{same}", flush=True)
     eng.close()
