@@ -285,6 +285,12 @@ def reference_arm(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # this arm is the reference's CPU path (the tier's contract for --impl reference); the reference's own GPU kernels,
+        # run unmodified on the same box, are reported by the default arm under "reference_gpu"
+        "reference_kind": "cpu: " + ("unmodified reference CPU functions (oracle/_ref/libqtref.so: Phi scale, radix2NTTGS, pointwise, "
+                                     "radix2INTT, invPhi; NTT.cu:1058-1084, 1473-1494, 1826-1849), OpenMP over polynomial pairs"
+                                     if use_ref else "oracle/qt_oracle.c port of the reference CPU functions"),
+        "reference_gpu_kernels": "see the default arm's `reference_gpu` key (oracle/_ref/ref_gpu_b65536 -speedgpu 6 and the same kernels, kernel-only)",
     }
     emit(line)
 

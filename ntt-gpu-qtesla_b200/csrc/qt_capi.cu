@@ -63,9 +63,14 @@ struct qt_ctx {
     uint64_t capture_launches0 = 0;
     // host pipeline (qt_polymul_host): lazily created
     static constexpr int PIPE = 8;  // maximum number of pipeline slots
-    int pipe_slots = 3;             // slots in use
+    int pipe_slots = 4;             // slots in use
+    bool pipe_ramp = true;          // small chunks at both ends of a large batch (QT_PIPE_RAMP=0 switches it off)
     cudaStream_t pipe_stream[PIPE] = {};
     uint32_t* pipe_buf[PIPE] = {};  // x | y per slot, z overwrites x
+    // role streams of the pinned pipeline (H2D / kernels / D2H) and the per-slot events that chain them
+    cudaStream_t role_stream[3] = {};
+    cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {}, ev_out[PIPE] = {};
+    bool pipe_roles = true;         // QT_PIPE_ROLES=0: one stream per slot (the round-1 structure)
     size_t pipe_polys = 0;
     bool pipe_ready = false;
     // staged pipeline for PAGEABLE host buffers (what a malloc-ing caller such as the reference's main.cu
@@ -381,8 +386,16 @@ void release_pipe(qt_ctx* c) {
     for (int i = 0; i < qt_ctx::PIPE; i++) {
         if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
         if (c->pipe_stream[i]) cudaStreamDestroy(c->pipe_stream[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
         c->pipe_buf[i] = nullptr;
         c->pipe_stream[i] = nullptr;
+        c->ev_in[i] = c->ev_k[i] = c->ev_out[i] = nullptr;
+    }
+    for (int i = 0; i < 3; i++) {
+        if (c->role_stream[i]) cudaStreamDestroy(c->role_stream[i]);
+        c->role_stream[i] = nullptr;
     }
     c->pipe_ready = false;
 }
@@ -444,14 +457,26 @@ int ensure_pipe(qt_ctx* c) {
         const size_t w = strtoull(e, nullptr, 10);
         if (w >= c->p.n) c->pipe_polys = w / c->p.n;
     }
+    if (const char* e = getenv("QT_PIPE_RAMP")) c->pipe_ramp = atoi(e) != 0;  // tuning aid
     if (const char* e = getenv("QT_PIPE_SLOTS")) {  // tuning aid
         const int k = atoi(e);
         if (k >= 1 && k <= qt_ctx::PIPE) c->pipe_slots = k;
     }
+    if (const char* e = getenv("QT_PIPE_ROLES")) c->pipe_roles = atoi(e) != 0;  // tuning aid
     for (int i = 0; i < c->pipe_slots; i++) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&c->pipe_buf[i], 2 * c->pipe_polys * c->p.n * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
         if (e != cudaSuccess) {  // leave no half-built pipeline behind
+            release_pipe(c);
+            return (int)e;
+        }
+    }
+    for (int i = 0; i < 3; i++) {
+        const cudaError_t e = cudaStreamCreateWithFlags(&c->role_stream[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
             release_pipe(c);
             return (int)e;
         }
@@ -753,27 +778,59 @@ static int host_pipeline(qt_ctx* c, const uint32_t* x, const uint32_t* y, uint32
     // smaller chunks for small batches (about two per slot) so that H2D, kernel and D2H still overlap
     const size_t chunk = std::min(cap, std::max<size_t>(std::max<size_t>(1, (128u << 10) / n),
                                                          (B + 2 * c->pipe_slots - 1) / (2 * c->pipe_slots)));
-    size_t done = 0;
+    // Large batches: the pipeline is full only between the first kernel and the last copy back, so the first chunks
+    // are small (the first kernel starts after 1/8 of a chunk has arrived instead of a whole one) and so are the
+    // last (the final device-to-host copy is short): cap/8, cap/8, cap/4, cap/2, cap ... cap, cap/2, cap/4, cap/8, cap/8.
+    // Measured on the 768 MiB step of the bench: 11.27 -> see DESIGN.md (bare concurrent copies: 10.3 ms).
+    const bool ramp = c->pipe_ramp && chunk == cap && cap >= 8 && B >= 6 * cap;
+    size_t done = 0, chunk_no = 0;
     int slot = 0;
+    const bool roles = c->pipe_roles;
     while (done < B && !rc) {
-        const size_t cnt = std::min(chunk, B - done);
+        size_t cnt = std::min(chunk, B - done);
+        if (ramp) {
+            const size_t left = B - done;
+            const size_t front = done < cap / 4 ? cap / 8 : done < cap / 2 ? cap / 4 : done < cap ? cap / 2 : cap;
+            const size_t back = left <= cap / 4 ? cap / 8 : left <= cap / 2 ? cap / 4 : left <= cap ? cap / 2 : cap;
+            cnt = std::min(std::min(front, back), left);
+        }
         const size_t bytes = cnt * n * sizeof(uint32_t);
-        cudaStream_t s = c->pipe_stream[slot];
         uint32_t* dx = c->pipe_buf[slot];
         uint32_t* dy = dx + cap * n;
-        rc = (int)cudaMemcpyAsync(dx, x + done * n, bytes, cudaMemcpyHostToDevice, s);
-        if (!rc) rc = (int)cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s);
-        if (!rc) {
-            if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s, OVL_YES);
-            else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, c->nuss_variant, s); if (!rc) c->launches++; }
+        // One stream per ROLE (all host-to-device copies in order on the first, the kernels on the second, the copies
+        // back on the third), chained per slot by events: the copy engines then see two plain queues.  With one stream
+        // per slot a host-to-device copy that waits for its slot sits in front of copies that could go
+        // (tools/pipe_probe.cu: 11.6 -> 11.0 ms for the 768 MiB step without any arithmetic; bare copies 10.25 ms).
+        cudaStream_t s_in = roles ? c->role_stream[0] : c->pipe_stream[slot];
+        cudaStream_t s_k = roles ? c->role_stream[1] : s_in, s_out = roles ? c->role_stream[2] : s_in;
+        if (roles && chunk_no >= (size_t)c->pipe_slots) rc = (int)cudaStreamWaitEvent(s_in, c->ev_out[slot], 0);  // slot free again
+        if (!rc) rc = (int)cudaMemcpyAsync(dx, x + done * n, bytes, cudaMemcpyHostToDevice, s_in);
+        if (!rc) rc = (int)cudaMemcpyAsync(dy, y + done * n, bytes, cudaMemcpyHostToDevice, s_in);
+        if (!rc && roles) {
+            rc = (int)cudaEventRecord(c->ev_in[slot], s_in);
+            if (!rc) rc = (int)cudaStreamWaitEvent(s_k, c->ev_in[slot], 0);
         }
-        if (!rc) rc = (int)cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s);
+        if (!rc) {
+            if (nuss_ring < 0) rc = QT_DISPATCH(c, launch_polymul, c, dx, dy, dx, cnt, s_k, OVL_YES);
+            else { rc = QT_DISPATCH(c, nuss_launch, c->grid_nuss, dx, dy, dx, cnt, nuss_ring, c->nuss_variant, s_k); if (!rc) c->launches++; }
+        }
+        if (!rc && roles) {
+            rc = (int)cudaEventRecord(c->ev_k[slot], s_k);
+            if (!rc) rc = (int)cudaStreamWaitEvent(s_out, c->ev_k[slot], 0);
+        }
+        if (!rc) rc = (int)cudaMemcpyAsync(z + done * n, dx, bytes, cudaMemcpyDeviceToHost, s_out);
+        if (!rc && roles) rc = (int)cudaEventRecord(c->ev_out[slot], s_out);
         done += cnt;
+        chunk_no++;
         slot = (slot + 1) % c->pipe_slots;
     }
     // always drain: the caller's buffers must not be touched after we return, error or not
     for (int i = 0; i < c->pipe_slots; i++) {
         const cudaError_t e = cudaStreamSynchronize(c->pipe_stream[i]);
+        if (!rc && e != cudaSuccess) rc = (int)e;
+    }
+    for (int i = 0; i < 3; i++) {
+        const cudaError_t e = cudaStreamSynchronize(c->role_stream[i]);
         if (!rc && e != cudaSuccess) rc = (int)e;
     }
     return rc;

@@ -27,7 +27,7 @@ for w in $WHICH; do
     fused)      cap fused      k_polymul_tma   4 python bench.py --steps 5 --warmup 3 --no-extras ;;
     fusedI)     cap fusedI     k_polymul_tma   4 python bench.py --steps 5 --warmup 3 --no-extras --set I ;;
     fusedpI)    cap fusedpI    k_polymul_tma   4 python bench.py --steps 5 --warmup 3 --no-extras --set p-I ;;
-    fusedpIII)  cap fusedpIII  k_polymul_split 4 python bench.py --steps 5 --warmup 3 --no-extras --set p-III ;;
+    fusedpIII)  cap fusedpIII  k_polymul_pair 4 python bench.py --steps 5 --warmup 3 --no-extras --set p-III ;;
     nussF64)    cap nussF64    k_nussbaumer_warp 2 python tools/nuss_one.py III 1 3 ;;
     nussRing)   cap nussRing   k_nussbaumer_warp 2 python tools/nuss_one.py III 0 0 ;;
     nussRec)    cap nussRec    k_nussbaumer_warp 2 python tools/nuss_one.py III 1 2 ;;
