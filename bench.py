@@ -702,11 +702,11 @@ def main():
         mi_, ri_ = (8, 8) if r_ == 64 else (4, 8)
         school_mults, rec_mults = 2 * m_ * r_ * r_, 2 * m_ * 2 * mi_ * ri_ * ri_
         small_q = p.q < (1 << 25)
-        nuss_defs = (("ring_2p32m1", qt.RING_2P32M1, 0, school_mults, 2, "k_nussbaumer_warp<1, 0, 0>"),
+        nuss_defs = (("ring_2p32m1", qt.RING_2P32M1, 0, school_mults, 2, "k_nussbaumer_warp<1, 0, 0, 0"),
                      ("mod_q", qt.RING_MODQ, 0, school_mults if small_q else rec_mults, 1 if small_q else 2, None),
-                     ("mod_q_schoolbook_rows", qt.RING_MODQ, 1, school_mults, 2, "k_nussbaumer_warp<1, 1, 0>"),
-                     ("mod_q_recursive_rows", qt.RING_MODQ, 2, rec_mults, 2, "k_nussbaumer_warp<1, 1, 1>"),
-                     ("mod_q_fp64_rows", qt.RING_MODQ, 3, school_mults, 1, "k_nussbaumer_warp<1, 1, 2>"),
+                     ("mod_q_schoolbook_rows", qt.RING_MODQ, 1, school_mults, 2, "k_nussbaumer_warp<1, 1, 0"),
+                     ("mod_q_recursive_rows", qt.RING_MODQ, 2, rec_mults, 2, "k_nussbaumer_warp<1, 1, 1"),
+                     ("mod_q_fp64_rows", qt.RING_MODQ, 3, school_mults, 1, "k_nussbaumer_warp<1, 1, 2"),
                      ("ring_2p32m1_lift_q (sparse / small operands, exact under its precondition)", qt.RING_2P32M1_LIFT_Q, 0,
                       school_mults, 2, None))
         for rname, ring, nv, mults, slots, kname in nuss_defs:
