@@ -769,8 +769,13 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
         const uint32_t* gy = y + p * K::N;
 #if QT_NUSS_PREFETCH
         if (p + (size_t)gridDim.x * W::WARPS < batch) {  // the next polynomial of this warp: its lines towards L2 now
+#if QT_NUSS_PREFETCH == 2
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(gx + (size_t)gridDim.x * W::WARPS * K::N + K::M * lane));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(gy + (size_t)gridDim.x * W::WARPS * K::N + K::M * lane));
+#else
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gx + (size_t)gridDim.x * W::WARPS * K::N + K::M * lane));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + (size_t)gridDim.x * W::WARPS * K::N + K::M * lane));
+#endif
         }
 #endif
         uint32_t v[W::ROWS];
