@@ -122,11 +122,11 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
     c->occ_fused = occ;
     c->grid_fused = occ * c->num_sms;
     c->smem_tma = StageShape<SET>::SMEM;
-    c->tma_warps = TmaCfg<SET>::WARPS;
+    c->tma_warps = TmaCfg<SET>::FUSED_WARPS;
     c->occ_tma = 0;
     if (cudaFuncSetAttribute(k_polymul_tma<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM) == cudaSuccess) {
         int o2 = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_polymul_tma<SET>, TmaCfg<SET>::WARPS * 32, StageShape<SET>::SMEM) == cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_polymul_tma<SET>, TmaCfg<SET>::FUSED_WARPS * 32, StageShape<SET>::SMEM) == cudaSuccess)
             c->occ_tma = o2;
     } else {
         (void)cudaGetLastError();
@@ -259,9 +259,9 @@ static StageGeom stage_geom(const qt_ctx* c, size_t tiles, int max_warps, size_t
     g.smem = table_bytes + (size_t)g.warps * warp_bytes + extra;
     return g;
 }
-template <int SET> static StageGeom stage_geom_set(const qt_ctx* c, size_t tiles, size_t extra = 0) {
+template <int SET> static StageGeom stage_geom_set(const qt_ctx* c, size_t tiles, size_t extra = 0, int max_warps = TmaCfg<SET>::WARPS) {
     using G = StageShape<SET>;
-    return stage_geom(c, tiles, TmaCfg<SET>::WARPS, KernelShape<SET>::TW_BYTES, G::BUFS * G::WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t), extra);
+    return stage_geom(c, tiles, max_warps, KernelShape<SET>::TW_BYTES, G::BUFS * G::WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t), extra);
 }
 static StageGeom stage_geom_split(const qt_ctx* c, size_t tiles, size_t extra = 0) {
     return stage_geom(c, tiles, SplitShape::WARPS, SplitShape::TW_BYTES, 2 * SplitShape::WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t), extra);
@@ -284,7 +284,7 @@ template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32
         cudaError_t e = launch_pdl(c, known, k_polymul_split<0>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab_split);
         if (e != cudaSuccess) return (int)e;
     } else if (tma) {
-        const StageGeom g = stage_geom_set<SET>(c, tiles);
+        const StageGeom g = stage_geom_set<SET>(c, tiles, 0, TmaCfg<SET>::FUSED_WARPS);
         cudaError_t e = launch_pdl(c, known, k_polymul_tma<SET>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab[1]);
         if (e != cudaSuccess) return (int)e;
     }

@@ -44,8 +44,22 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// Warps per CTA of the FUSED kernel, per parameter set (run r02t; only multiples of four — the four schedulers of an SM
+// must get the same number of warps: 18 and 22 lose 8-10 %):
+//   qTESLA-III : 16 / 20 / 24 warps -> 243.3 / 245.5 / 243.1 M polymul/s
+//   qTESLA-p-I : 16 / 20 / 24 warps -> 209.3 / 211.0 / 214.0  (24 warps = 80 registers, 16 bytes of spill, still faster)
+//   qTESLA-I   : 16 / 20 / 24 warps -> 505.5 / 505.7 / 493.5
+#ifndef QT_FUSED_WARPS_III
+#define QT_FUSED_WARPS_III 20
+#endif
+#ifndef QT_FUSED_WARPS_P_I
+#define QT_FUSED_WARPS_P_I 24
+#endif
 template <int SET> struct TmaCfg {
-    static constexpr int WARPS = (Cfg<SET>::E == 64) ? QT_TMA_WARPS_E64 : QT_TMA_WARPS;
+    static constexpr int WARPS = (Cfg<SET>::E == 64) ? QT_TMA_WARPS_E64 : QT_TMA_WARPS;   // single transforms, cached-transform product
+    static constexpr int FUSED_WARPS = (Cfg<SET>::E == 64) ? QT_TMA_WARPS_E64
+                                       : SET == SET_III ? QT_FUSED_WARPS_III : SET == SET_P_I ? QT_FUSED_WARPS_P_I : QT_TMA_WARPS;
+    static constexpr int MAX_WARPS = WARPS > FUSED_WARPS ? WARPS : FUSED_WARPS;
     static constexpr int MINB = (Cfg<SET>::E == 64) ? 1 : QT_TMA_MINB;  // 64 coefficients per thread need the registers
 };
 
@@ -165,8 +179,8 @@ template <int SET> struct StageShape {
     static constexpr uint32_t POLY_STRIDE = T::N + PAD;      // words
     static constexpr uint32_t WORDS = T::PPW * POLY_STRIDE;  // one buffer (>= TILE_WORDS)
     static constexpr uint32_t BUFS = 2 + QT_TMA_STORE;       // x staging, y staging (+ z staging for the bulk-store variant)
-    static constexpr size_t SMEM = KernelShape<SET>::TW_BYTES + (size_t)TmaCfg<SET>::WARPS * BUFS * WORDS * sizeof(uint32_t) +
-                                   (size_t)TmaCfg<SET>::WARPS * 2 * sizeof(uint64_t);
+    static constexpr size_t SMEM = KernelShape<SET>::TW_BYTES + (size_t)TmaCfg<SET>::MAX_WARPS * BUFS * WORDS * sizeof(uint32_t) +
+                                   (size_t)TmaCfg<SET>::MAX_WARPS * 2 * sizeof(uint64_t);
     static constexpr size_t SMEM_BCAST = SMEM + T::N * sizeof(uint32_t);  // + the broadcast a_hat of k_polymul_ntt
     static __device__ __forceinline__ uint32_t off(uint32_t lane, uint32_t r) {
         return (lane / T::LPP) * POLY_STRIDE + (lane % T::LPP) + T::LPP * r;
@@ -174,7 +188,7 @@ template <int SET> struct StageShape {
 };
 
 template <int SET>
-__global__ void __launch_bounds__(TmaCfg<SET>::WARPS * 32, TmaCfg<SET>::MINB)
+__global__ void __launch_bounds__(TmaCfg<SET>::FUSED_WARPS * 32, TmaCfg<SET>::MINB)
 k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwQuad* __restrict__ g_lane) {
     using T = Tile<SET>;
     using S = KernelShape<SET>;

@@ -85,13 +85,13 @@ struct alignas(16) U4 { uint32_t x, y, z, w; };  // 128-bit shared-memory access
 // level, the y input is reset to [0, 2q) by its Shoup multiplication; in the Gentleman-Sande inverse the sum output
 // adds the two bounds and the product output is reset.  The plan below runs that bookkeeping at COMPILE TIME over the
 // unrolled butterfly network of one thread and records where a conditional subtraction is really needed (and by how
-// many q): 308 instead of 576 per product and thread for n = 1024.  Bounds are in units of q ("b" means value < b q);
+// many q): 276 instead of 576 per product and thread for n = 1024.  Bounds are in units of q ("b" means value < b q);
 // at the shared-memory transpositions the worst register's bound is taken for all (a thread's registers there come
 // from different registers of 32 other threads).
 template <uint32_t E, uint32_t LB1, uint32_t LB2, uint32_t CAP> struct HarveyPlan {
     struct P {
         uint8_t fr[LB1][E / 2];     // forward, rows levels: csub modulus (x q) applied to x before butterfly i, 0 = none
-        uint8_t fc[LB2][E / 2];     // forward, cols levels
+        uint8_t fc[LB2][E / 2][3];  // forward, cols levels: a chain of up to three (the last level reduces x to [0, 2q), see make())
         uint8_t fout[E];            // bounds of the forward output
         uint8_t pwa[E][3], pwb[E][3];  // pointwise product of two forward outputs: csub chains of either operand
         uint8_t cf[E][4];           // forward output -> canonical: csub chain down to 1
@@ -122,10 +122,14 @@ template <uint32_t E, uint32_t LB1, uint32_t LB2, uint32_t CAP> struct HarveyPla
         for (uint32_t r = 0; r < E; r++) b[r] = u;
         for (uint32_t k = 0; k < LB2; k++) {
             const uint32_t half = (E >> 1) >> k;
+            // the LAST level brings x down to [0, 2q) first: both outputs are then below 4q and the pointwise product
+            // needs one correction per pair instead of four (64 + 32 instead of 32 + 128 corrections per thread)
+            const uint32_t lim = (k + 1 == LB2) ? 2 : CAP - 2;
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t x = 2 * (i / half) * half + i % half, y = x + half;
-                if (b[x] + 2 > CAP) { p.fc[k][i] = (uint8_t)halve(b[x]); b[x] = halve(b[x]); }
-                if (b[x] + 2 > CAP) p.ok = 0;
+                uint32_t n = 0;
+                while (b[x] > lim && n < 3) { p.fc[k][i][n++] = (uint8_t)halve(b[x]); b[x] = halve(b[x]); }
+                if (b[x] > lim) p.ok = 0;
                 b[x] += 2; b[y] = b[x];
             }
         }
@@ -318,8 +322,9 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
     }
     template <uint32_t K, uint32_t I> static QT_HD void h_fc(uint32_t (&v)[E], const TwQuad* tw) {
         constexpr uint32_t half = (E >> 1) >> K, G = E / (2 * half), g = I / half, X = 2 * g * half + I % half, Y = X + half;
-        constexpr uint32_t m = HPlan::make().fc[K][I];
-        const uint32_t wy = mul_shoup(v[Y], lane_slot(tw, G - G0 + g, BLOCKS)), xx = csub_q<m>(v[X]);
+        constexpr auto pl = HPlan::make();
+        const uint32_t wy = mul_shoup(v[Y], lane_slot(tw, G - G0 + g, BLOCKS));
+        const uint32_t xx = csub_q<pl.fc[K][I][2]>(csub_q<pl.fc[K][I][1]>(csub_q<pl.fc[K][I][0]>(v[X])));
         v[X] = xx + wy;
         v[Y] = xx - wy + TWO_Q;
     }
