@@ -593,6 +593,10 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
     // ranges of the lazy variant: 32 products of two forward outputs in an int64; 3 * 2^(LOGM+1) q in an int32
     static_assert(!LAZYQ || (uint64_t)Q * Q < (1ull << (63 - 5 - 2 * LOGM)), "lazy product accumulator");
     static_assert(!LAZYQ || ((uint64_t)(3u << (LOGM + 1)) * Q < (1ull << 31)), "lazy inverse range");
+#ifndef QT_NUSS_SIGN_MAD
+#define QT_NUSS_SIGN_MAD 1
+#endif
+    static constexpr bool SIGN_MAD = QT_NUSS_SIGN_MAD && F64;            // signed rotations as multiply-adds (forward() below)
     static constexpr uint32_t RS = 33;                                   // row stride in shared memory
     static constexpr uint32_t WARP_WORDS = 2 * ROWS * RS;                // X rows then Y rows
 #ifndef QT_NUSS_WARPS
@@ -622,11 +626,21 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                 const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
                 const uint32_t I = (i << (j + 1)) + t, L = I + (1u << j), sr = rot(i, (uint32_t)j);
                 uint32_t tv = v[L];
+                const uint32_t vi = v[I];
+                if (SIGN_MAD && sr != 0) {
+                    // FP64-row kernel: the integer multiply pipe is nearly idle (23 %), the issue slots are what is scarce.
+                    // The sign of the rotated row becomes a +-1 multiplier (one register pair per rotation amount), and a
+                    // row butterfly is SHFL + 2 multiply-adds instead of SHFL + negate + select + add + subtract.
+                    const uint32_t src = __shfl_sync(0xffffffffu, tv, (lane - sr) & 31u);
+                    const uint32_t sg = (lane >= sr) ? 1u : 0xFFFFFFFFu;
+                    v[I] = src * sg + vi;
+                    v[L] = src * (0u - sg) + vi;
+                    continue;
+                }
                 if (sr != 0) {  // X_l * w^sr: coefficient a comes from a - sr, negated on wrap-around
                     const uint32_t src = __shfl_sync(0xffffffffu, tv, (lane - sr) & 31u);
                     tv = (lane >= sr) ? src : O::neg(src);
                 }
-                const uint32_t vi = v[I];
                 v[L] = O::sub(vi, tv);
                 v[I] = O::add(vi, tv);
             }
@@ -646,7 +660,8 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                 z[A] = O::half(O::add(za, zb));
                 if (sr != 0) {  // Z_B = T * w^-sr: coefficient a takes T[a + sr], negated on wrap-around
                     const uint32_t src = __shfl_sync(0xffffffffu, tv, (lane + sr) & 31u);
-                    tv = (lane < 32u - sr) ? src : O::neg(src);
+                    if (SIGN_MAD) tv = src * ((lane < 32u - sr) ? 1u : 0xFFFFFFFFu);  // (lazy: half() is the identity)
+                    else tv = (lane < 32u - sr) ? src : O::neg(src);
                 }
                 z[B] = tv;
             }

@@ -356,6 +356,26 @@ template <int SET> int emu_row_f64(const uint32_t* x, const uint32_t* y, uint32_
     }
 
 extern "C" {
+// static range plan of the Harvey path (qt_tile.cuh: HarveyPlan) for qTESLA-p-I: out = {ok, corrections in one forward
+// transform, in the pointwise product of two forward outputs, in the inverse transform, largest forward-output bound,
+// bound carried across the forward transposition, bound carried across the inverse transposition, 2^32 / q}
+int qtemu_harvey_plan(uint32_t* out) {
+    using T = qt::Tile<qt::SET_P_I>;
+    static_assert(T::HLAZY, "qTESLA-p-I runs the range plan");
+    constexpr auto p = T::HPlan::make();
+    uint32_t f = 0, w = 0, v = 0, m = 0;
+    for (uint32_t l = 0; l < T::LB1; l++) for (uint32_t i = 0; i < T::E / 2; i++) f += p.fr[l][i] != 0;
+    for (uint32_t k = 0; k < T::LB2; k++) for (uint32_t i = 0; i < T::E / 2; i++) for (int c = 0; c < 3; c++) f += p.fc[k][i][c] != 0;
+    for (uint32_t r = 0; r < T::E; r++) {
+        for (int c = 0; c < 3; c++) w += (p.pwa[r][c] != 0) + (p.pwb[r][c] != 0);
+        m = p.fout[r] > m ? p.fout[r] : m;
+    }
+    for (uint32_t k = 0; k < T::LB2; k++) for (uint32_t i = 0; i < T::E / 2; i++) v += (p.ic[k][i][0] != 0) + (p.ic[k][i][1] != 0);
+    for (uint32_t k = 0; k < T::LB1; k++) for (uint32_t i = 0; i < T::E / 2; i++) v += (p.ir[k][i][0] != 0) + (p.ir[k][i][1] != 0);
+    out[0] = p.ok; out[1] = f; out[2] = w; out[3] = v; out[4] = m; out[5] = p.rows_out; out[6] = p.icols_out; out[7] = T::QCAP;
+    return 0;
+}
+
 int qtemu_polymul(int set, const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch) {
     EMU_DISPATCH(set, polymul(x, y, z, batch));
     return 0;

@@ -196,3 +196,17 @@ def test_fp64_row_product_exact(emu, oracle, s):
     zs = z.view(np.int32).astype(np.int64).reshape(rows, 32)
     assert np.abs(zs).max() <= q // 2 + 1
     assert np.array_equal(zs % q, _negacyclic_rows(x, y, q))
+
+
+def test_harvey_range_plan_of_p_I(emu):
+    """the compile-time range plan of the 29-bit modulus (HarveyPlan, qt_tile.cuh): no value can leave 32 bits
+    (every bound <= floor((2^32-1)/q) = 12), and it needs 276 conditional subtractions per product and thread where the
+    classic [0,4q) butterflies need 576"""
+    out = (C.c_uint32 * 8)()
+    assert emu.qtemu_harvey_plan(out) == 0
+    ok, fwd, pw, inv, fout_max, rows_out, icols_out, cap = list(out)
+    assert ok == 1 and cap == 12
+    assert max(fout_max, rows_out, icols_out) <= cap
+    assert (fwd, pw, fout_max) == (64, 32, 4)      # forward: 5 free levels, 32 + 32 corrections; one correction per pointwise pair
+    assert inv == 84 and rows_out == 11
+    assert 2 * fwd + pw + inv + 32 == 276          # + the 32 final subtractions that make the output canonical

@@ -304,3 +304,73 @@ def test_graph_api_misuse_is_an_error(qt):
         e.graph_destroy(g)
     finally:
         e.close()
+
+
+# ---- guard-band check (compute-sanitizer is closed on this pool): no entry point writes outside its operands -------
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+def test_no_write_outside_the_output_arrays(qt, s):
+    """every device-pointer entry point on ragged batches, outputs embedded in sentinel-filled guard bands (also right
+    after the LAST polynomial of a partial tile — where a mis-sized bulk copy or an unmasked store would land)"""
+    import torch
+    e = qt.Engine(s, 0)
+    try:
+        n, GUARD, SENT = e.n, 4096, 0x5A5A5A5A
+        for B in (1, 3, 17, 149, 297, 1777):
+            words = B * n
+
+            def guarded():
+                t = torch.full((words + 2 * GUARD,), SENT, dtype=torch.int32, device="cuda")
+                return t, t[GUARD: GUARD + words]
+
+            def intact(t):
+                return bool((t[:GUARD] == SENT).all()) and bool((t[GUARD + words:] == SENT).all())
+            x = torch.empty(words, dtype=torch.int32, device="cuda")
+            y = torch.empty_like(x)
+            e.fill_uniform(x, 1, 0)
+            e.fill_uniform(y, 2, 0)
+            e.synchronize()
+            variants = (0, 1, 2) + ((3, 4) if s == 3 else ())
+            for v in variants:
+                e.set_fused_variant(v)
+                zt, z = guarded()
+                e.polymul(x, y, z, B)
+                e.synchronize()
+                assert intact(zt), ("polymul", v, B)
+            e.set_fused_variant(0)
+            for name, fn in (("ntt_forward", e.ntt_forward), ("ntt_inverse", e.ntt_inverse),
+                             ("ntt_forward_natural", e.ntt_forward_natural), ("ntt_inverse_natural", e.ntt_inverse_natural)):
+                wt, w = guarded()
+                w.copy_(x)
+                torch.cuda.synchronize()
+                fn(w, B)
+                e.synchronize()
+                assert intact(wt), (name, B)
+            wt, w = guarded()
+            e.pointwise(x, y, w, B)
+            e.synchronize()
+            assert intact(wt), ("pointwise", B)
+            wt, w = guarded()
+            e.bitrev_copy(x, w, B)
+            e.synchronize()
+            assert intact(wt), ("bitrev_copy", B)
+            ah = x[:n].clone()
+            e.ntt_forward(ah, 1)
+            for bc, a in ((True, ah), (False, x)):
+                wt, w = guarded()
+                e.polymul_ntt(a, y, w, bc, B)
+                e.synchronize()
+                assert intact(wt), ("polymul_ntt", bc, B)
+            for ring in (qt.RING_2P32M1, qt.RING_MODQ, qt.RING_2P32M1_LIFT_Q):
+                for nv in (0, 1, 2, 16, 18):
+                    e.set_nussbaumer_variant(nv)
+                    wt, w = guarded()
+                    e.nussbaumer(x, y, w, ring, B)
+                    e.synchronize()
+                    assert intact(wt), ("nussbaumer", ring, nv, B)
+            e.set_nussbaumer_variant(0)
+            wt, w = guarded()
+            e.fill_uniform(w, 3, 0)
+            e.synchronize()
+            assert intact(wt), ("fill_uniform", B)
+    finally:
+        e.close()
