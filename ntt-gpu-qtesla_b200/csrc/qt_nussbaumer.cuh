@@ -594,7 +594,7 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
     static_assert(!LAZYQ || (uint64_t)Q * Q < (1ull << (63 - 5 - 2 * LOGM)), "lazy product accumulator");
     static_assert(!LAZYQ || ((uint64_t)(3u << (LOGM + 1)) * Q < (1ull << 31)), "lazy inverse range");
 #ifndef QT_NUSS_SIGN_MAD
-#define QT_NUSS_SIGN_MAD 1
+#define QT_NUSS_SIGN_MAD 0  // measured (run r02w): 80.9 vs 87.5 M polymul/s at n=1024, 210.8 vs 219.4 at n=512 — rejected, kept for A/B
 #endif
     static constexpr bool SIGN_MAD = QT_NUSS_SIGN_MAD && F64;            // signed rotations as multiply-adds (forward() below)
     static constexpr uint32_t RS = 33;                                   // row stride in shared memory
@@ -628,9 +628,8 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                 uint32_t tv = v[L];
                 const uint32_t vi = v[I];
                 if (SIGN_MAD && sr != 0) {
-                    // FP64-row kernel: the integer multiply pipe is nearly idle (23 %), the issue slots are what is scarce.
-                    // The sign of the rotated row becomes a +-1 multiplier (one register pair per rotation amount), and a
-                    // row butterfly is SHFL + 2 multiply-adds instead of SHFL + negate + select + add + subtract.
+                    // A/B variant (off): the sign of the rotated row as a +-1 multiplier, a row butterfly = SHFL + 2 multiply-adds
+                    // instead of SHFL + negate + select + add + subtract.  Fewer instructions, but slower (see QT_NUSS_SIGN_MAD).
                     const uint32_t src = __shfl_sync(0xffffffffu, tv, (lane - sr) & 31u);
                     const uint32_t sg = (lane >= sr) ? 1u : 0xFFFFFFFFu;
                     v[I] = src * sg + vi;
