@@ -374,3 +374,62 @@ def test_no_write_outside_the_output_arrays(qt, s):
             assert intact(wt), ("fill_uniform", B)
     finally:
         e.close()
+
+
+def test_graph_with_every_recordable_entry_point(qt, oracle):
+    """one graph holding a transform round trip, a pointwise product, a bit-reverse copy, a Nussbaumer product over Z_q,
+    the ring lift and a cached-transform product; replayed and compared with the oracle"""
+    import torch
+    s = 1
+    e = qt.Engine(s, 0)
+    try:
+        n, q, B = e.n, e.q, 53
+        rng = np.random.default_rng(9)
+        x, y = rand_pair(q, B * n, 91)
+        c = ternary(rng, q, n, B, 48)
+        dev = lambda a: torch.from_numpy(a.view(np.int32)).cuda()
+        tx, ty, tc = dev(x), dev(y), dev(c)
+        w, pw, br, nz, lf, ca = (torch.empty_like(tx) for _ in range(6))
+        ah = tx[:n].clone()
+        torch.cuda.synchronize()
+        e.graph_begin()
+        e.ntt_forward(ah, 1)
+        e.polymul_ntt(ah, ty, ca, True, B)      # ca = x[0] * y[b]
+        e.pointwise(tx, ty, pw, B)
+        e.bitrev_copy(tx, br, B)
+        e.nussbaumer(tx, ty, nz, qt.RING_MODQ, B)
+        e.nussbaumer(tx, tc, lf, qt.RING_2P32M1_LIFT_Q, B)
+        e.polymul(tx, ty, w, B)
+        e.ntt_forward(w, B)
+        e.ntt_inverse(w, B)
+        g = e.graph_end()
+        assert e.graph_kernel_count(g) == 9
+        for _ in range(2):
+            ah.copy_(tx[:n])
+            torch.cuda.synchronize()
+            e.graph_launch(g)
+            e.synchronize()
+        host = lambda t: t.cpu().numpy().view(np.uint32)
+        ref = oracle.polymul(s, x, y, threads=0)
+        assert np.array_equal(host(w), ref) and np.array_equal(host(nz), ref)
+        assert np.array_equal(host(pw), oracle.pointwise(s, x, y))
+        assert np.array_equal(host(br), oracle.bitrev_copy(s, x))
+        assert np.array_equal(host(lf), oracle.polymul(s, x, c, threads=0))
+        assert np.array_equal(host(ca), oracle.polymul(s, np.tile(x[:n], B), y, threads=0))
+        e.graph_destroy(g)
+    finally:
+        e.close()
+
+
+def test_ring_lift_through_the_host_pointer_form(qt, oracle):
+    e = qt.Engine(0, 0)
+    try:
+        rng = np.random.default_rng(12)
+        B = 700
+        small = rng.integers(-2000, 2001, B * e.n)
+        xs = np.where(small < 0, small + e.q, small).astype(np.uint32)
+        c = ternary(rng, e.q, e.n, B, 30)
+        z = e.nussbaumer_host(xs, c, ring=qt.RING_2P32M1_LIFT_Q)
+        assert np.array_equal(z, oracle.polymul(0, xs, c, threads=0))
+    finally:
+        e.close()
