@@ -508,7 +508,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the other parameter sets / CPU baseline")
     ap.add_argument("--launch-overlap", type=int, default=0, choices=[0, 1, 2],
                     help="programmatic dependent launch of the fused kernel: 0 automatic (on), 1 never, 2 always")
-    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3, 4],
+    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
                     help="fused-kernel data path: 0 automatic, 1 direct coalesced loads, 2 TMA-staged")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -22,12 +22,16 @@
 
 namespace qt {
 TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
+double h_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];
 }
 
 using namespace qt;
 
 #ifndef QT_AUTO_PREFERS_TMA
 #define QT_AUTO_PREFERS_TMA 1
+#endif
+#ifndef QT_AUTO_PREFERS_DQ
+#define QT_AUTO_PREFERS_DQ 0  // signed-lazy sets: the FP64-quotient fused kernel (k_polymul_dq) rather than k_polymul_tma
 #endif
 #ifndef QT_AUTO_PREFERS_PAIR
 #define QT_AUTO_PREFERS_PAIR 1  // n = 2048: two warps per polynomial (k_polymul_pair) rather than one (k_polymul_split)
@@ -50,6 +54,8 @@ struct qt_ctx {
     int grid_fused = 0, grid_fwd = 0, grid_inv = 0, grid_nuss = 0, grid_tma = 0;
     int occ_fused = 0, occ_tma = 0, tma_warps = 0;
     TwQuad* d_tab_split = nullptr;          // n=2048 only: tables of the split tile (k_polymul_split)
+    TwW2* d_tabW = nullptr;                 // signed-lazy sets: FP64-quotient companions of d_tab[1] (k_polymul_dq)
+    bool dq_ok = false;
     bool split_ok = false;
     bool pair_ok = false;                   // n=2048 only: two warps per polynomial (k_polymul_pair)
     int variant = 0;  // 0 auto, 1 direct loads, 2 TMA-staged, 3 split tile (n=2048)
@@ -132,6 +138,14 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
         (void)cudaGetLastError();
     }
     c->grid_tma = c->occ_tma * c->num_sms;
+    if constexpr (Cfg<SET>::LAZY) {
+        int o3 = 0;
+        if (c->d_tabW && cudaFuncSetAttribute(k_polymul_dq<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqShape<SET>::SMEM) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_polymul_dq<SET>, DqShape<SET>::WARPS * 32, DqShape<SET>::SMEM) == cudaSuccess)
+            c->dq_ok = o3 > 0;
+        else
+            (void)cudaGetLastError();
+    }
     (void)cudaFuncSetAttribute(k_ntt_tma<SET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
     (void)cudaFuncSetAttribute(k_ntt_tma<SET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageShape<SET>::SMEM);
     (void)cudaFuncSetAttribute(k_bitrev_copy<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BitrevShape<SET>::SMEM);
@@ -156,14 +170,19 @@ int upload_tables(qt_ctx* c) {
         QT_CUDA(cudaMalloc(&c->d_tab[k], bytes));
         QT_CUDA(cudaMemcpy(c->d_tab[k], T.block[k].data(), bytes, cudaMemcpyHostToDevice));
     }
+    if (!T.blockW[1].empty()) {
+        const size_t bytes = T.blockW[1].size() * sizeof(TwW2);
+        QT_CUDA(cudaMalloc(&c->d_tabW, bytes));
+        QT_CUDA(cudaMemcpy(c->d_tabW, T.blockW[1].data(), bytes, cudaMemcpyHostToDevice));
+    }
     {
         std::lock_guard<std::mutex> lk(g_uni_mutex);
         memcpy(h_uni[c->set], T.uni, sizeof(T.uni));
-        if (c->device < 64 && !g_uni_uploaded[c->device][c->set]) {
+        memcpy(h_uniW[c->set], T.uniW, sizeof(T.uniW));
+        if (c->device >= 64 || !g_uni_uploaded[c->device][c->set]) {
             QT_CUDA(cudaMemcpyToSymbol(c_uni, T.uni, sizeof(T.uni), (size_t)c->set * sizeof(T.uni)));
-            g_uni_uploaded[c->device][c->set] = true;
-        } else if (c->device >= 64) {
-            QT_CUDA(cudaMemcpyToSymbol(c_uni, T.uni, sizeof(T.uni), (size_t)c->set * sizeof(T.uni)));
+            QT_CUDA(cudaMemcpyToSymbol(c_uniW, T.uniW, sizeof(T.uniW), (size_t)c->set * sizeof(T.uniW)));
+            if (c->device < 64) g_uni_uploaded[c->device][c->set] = true;
         }
     }
     if (c->set == SET_P_III) {  // the split tile of the fused n=2048 kernel
@@ -283,6 +302,12 @@ template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32
         const StageGeom g = stage_geom_split(c, B);
         cudaError_t e = launch_pdl(c, known, k_polymul_split<0>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab_split);
         if (e != cudaSuccess) return (int)e;
+    } else if (Cfg<SET>::LAZY && c->dq_ok && aligned && (c->variant == 5 || (c->variant == 0 && QT_AUTO_PREFERS_DQ))) {
+        if constexpr (Cfg<SET>::LAZY) {
+            const StageGeom g = stage_geom(c, tiles, DqShape<SET>::WARPS, DqShape<SET>::TABLE_BYTES, DqShape<SET>::WARP_BYTES);
+            cudaError_t e = launch_pdl(c, known, k_polymul_dq<SET>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab[1], c->d_tabW);
+            if (e != cudaSuccess) return (int)e;
+        }
     } else if (tma) {
         const StageGeom g = stage_geom_set<SET>(c, tiles, 0, TmaCfg<SET>::FUSED_WARPS);
         cudaError_t e = launch_pdl(c, known, k_polymul_tma<SET>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab[1]);
@@ -571,6 +596,7 @@ int qt_destroy(qt_ctx* c) {
     for (int k = 0; k < 2; k++)
         if (c->d_tab[k]) cudaFree(c->d_tab[k]);
     if (c->d_tab_split) cudaFree(c->d_tab_split);
+    if (c->d_tabW) cudaFree(c->d_tabW);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -583,7 +609,8 @@ int qt_set_stream(qt_ctx* c, void* s) {
 }
 
 int qt_set_fused_variant(qt_ctx* c, int variant) {
-    if (!c || variant < 0 || variant > 4) return QT_ERR_BAD_ARG;
+    if (!c || variant < 0 || variant > 5) return QT_ERR_BAD_ARG;
+    if (variant == 5 && !c->dq_ok) return QT_ERR_UNSUPPORTED;
     if (variant == 2 && c->occ_tma < 1) return QT_ERR_UNSUPPORTED;
     if (variant == 3 && !c->split_ok) return QT_ERR_UNSUPPORTED;
     if (variant == 4 && !c->pair_ok) return QT_ERR_UNSUPPORTED;

@@ -301,6 +301,139 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
 #endif
 }
 
+// ---- FP64-quotient variant of the fused kernel (signed-lazy sets: qTESLA-I, qTESLA-III) ----------------------------
+// Same staging, same buffers, same transposition pattern as k_polymul_tma; the butterflies take their quotient estimate
+// from the FP64 pipe (Tile::ct_dq) instead of a mul.hi, which halves the multiply-pipe time of a product.  Values
+// are 64-bit register pairs with a zero high half (see qt_tile.cuh); the table block is followed by its TwW2 companion.
+#ifndef QT_DQ_WARPS
+#define QT_DQ_WARPS 16
+#endif
+template <int SET> struct DqShape {
+    using T = Tile<SET>;
+    using G = StageShape<SET>;
+    static constexpr int WARPS = QT_DQ_WARPS;
+    static constexpr size_t TWW_BYTES = KernelShape<SET>::TW_QUADS * sizeof(TwW2);
+    static constexpr size_t TABLE_BYTES = KernelShape<SET>::TW_BYTES + TWW_BYTES;
+    static constexpr size_t WARP_BYTES = 2 * G::WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t);
+    static constexpr size_t SMEM = TABLE_BYTES + (size_t)WARPS * WARP_BYTES;
+};
+
+template <int SET>
+__global__ void __launch_bounds__(DqShape<SET>::WARPS * 32, 1)
+k_polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwQuad* __restrict__ g_lane, const TwW2* __restrict__ g_laneW) {
+    using T = Tile<SET>;
+    using S = KernelShape<SET>;
+    using G = StageShape<SET>;
+    static_assert(T::LAZY && QT_TMA_STORE == 0, "FP64-quotient kernel: signed-lazy sets");
+    extern __shared__ uint4 smem_raw[];
+    __shared__ uint32_t s_zero[T::E];
+    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
+    TwW2* s_twW = reinterpret_cast<TwW2*>(s_tw + S::TW_QUADS);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_twW + S::TW_QUADS);
+    const int NW = (int)(blockDim.x >> 5);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* A = s_stage + warp * 2 * G::WORDS;
+    uint32_t* B = A + G::WORDS;
+    uint64_t* bar_a = s_bar + 2 * warp;
+    uint64_t* bar_b = bar_a + 1;
+    const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
+    const size_t stride = (size_t)gridDim.x * NW;
+    size_t tile = (size_t)warp * gridDim.x + blockIdx.x;
+
+    auto issue = [&](const uint32_t* g, uint32_t* st, uint64_t* bar, size_t t) {  // one lane
+        const size_t p0 = t * T::PPW;
+        const uint32_t np = (uint32_t)((batch - p0 < T::PPW) ? batch - p0 : T::PPW);
+        mbar_expect_tx(bar, np * T::N * (uint32_t)sizeof(uint32_t));
+        if (G::PAD == 0) {
+            bulk_g2s(st, g + p0 * T::N, np * T::N * (uint32_t)sizeof(uint32_t), bar);
+        } else {
+            for (uint32_t p = 0; p < np; p++)
+                bulk_g2s(st + p * G::POLY_STRIDE, g + (p0 + p) * T::N, T::N * (uint32_t)sizeof(uint32_t), bar);
+        }
+    };
+
+    pdl_launch_dependents();
+    if (lane == 0) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (threadIdx.x < T::E) s_zero[threadIdx.x] = 0u;
+    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
+    copy_table_to_smem(reinterpret_cast<TwQuad*>(s_twW), reinterpret_cast<const TwQuad*>(g_laneW), S::TW_QUADS);
+    pdl_wait();
+    if (lane == 0 && tile < ntiles) {
+        issue(x, A, bar_a, tile);
+        issue(y, B, bar_b, tile);
+    }
+    __syncthreads();
+
+    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
+    const typename T::LanePtrsW PW = T::lane_ptrs_w(s_twW, lane);
+    // a value = (zero high half loaded from s_zero) : (low half); re-made whenever the low halves are loaded, so that no
+    // register pair is carried around a loop (qt_tile.cuh)
+#define QT_DQ_PAIR(r, lo) ((((uint64_t) * (volatile uint32_t*)&s_zero[r]) << 32) | (uint64_t)(lo))  /* volatile: one LDS each, never a 128-bit load into four consecutive registers */
+    uint32_t phase = 0;
+    for (; tile < ntiles; tile += stride, phase ^= 1) {
+        const size_t base = tile * T::C::TILE_WORDS;
+        const bool valid = tile * T::PPW + lane / T::LPP < batch;
+        const bool more = tile + stride < ntiles;
+        uint64_t v[T::E];
+#pragma unroll 1
+        for (int op = 0; op < 2; op++) {  // one copy of the forward-transform code for x and y
+            uint32_t* st = op ? B : A;
+            mbar_wait(op ? bar_b : bar_a, phase);
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, st[G::off(lane, r)]);
+            __syncwarp();
+            T::fwd_rows_dq(v);
+            if (T::PPW == 2) {
+                const typename T::RowBases RB = T::row_bases(lane);
+#pragma unroll
+                for (uint32_t r = 0; r < T::E; r++) st[T::rows_addr(RB, r)] = (uint32_t)v[r];
+            } else {
+#pragma unroll
+                for (uint32_t r = 0; r < T::E; r++) st[T::swz(T::row_off(lane, r))] = (uint32_t)v[r];
+            }
+            __syncwarp();
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, st[T::swz(T::E * lane + r)]);
+            T::fwd_cols_dq(v, P.fwd, PW.fwd);
+            if (op == 0) {
+                __syncwarp();             // every lane has read its columns before A is overwritten
+#pragma unroll
+                for (uint32_t r = 0; r < T::E; r++) A[T::swz(T::E * lane + r)] = (uint32_t)v[r];  // stash NTT(x); each lane reads back only what it wrote
+            }
+        }
+        T::pointwise_dq_stash(v, A, lane);
+        fence_proxy_async();
+        __syncwarp();                     // A is free: fetch the next tile's x into it
+        if (more && lane == 0) issue(x, A, bar_a, tile + stride);
+        T::inv_cols_dq(v);
+#pragma unroll
+        for (uint32_t r = 0; r < T::E; r++) B[T::swz(T::E * lane + r)] = (uint32_t)v[r];
+        __syncwarp();
+        if (T::PPW == 2) {
+            const typename T::RowBases RB = T::row_bases(lane);
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, B[T::rows_addr(RB, r)]);
+        } else {
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, B[T::swz(T::row_off(lane, r))]);
+        }
+        fence_proxy_async();
+        __syncwarp();                     // B is free: fetch the next tile's y into it
+        if (more && lane == 0) issue(y, B, bar_b, tile + stride);
+        uint32_t out[T::E];
+        T::inv_rows_dq(v, out, P, PW);
+        T::store_rows(out, z + base, lane, valid);
+    }
+#undef QT_DQ_PAIR
+}
+
 // Fused product for n = 2048 (qTESLA-p-III) on the SPLIT tile: a polynomial is two 1024-point halves
 // joined by one level, and every transform runs the 32-coefficients-per-thread half code twice (a rolled
 // loop) instead of one 64-coefficients-per-thread pass.  Why: the 64-wide kernel is 7360 instructions

@@ -28,8 +28,10 @@
 // Everything here is __host__ __device__ so that tests/emu can execute the identical index
 // arithmetic and 32-bit wrap-around behaviour lane by lane on a CPU (test infrastructure only).
 #pragma once
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <utility>
 
 #include "qt_params.h"
@@ -47,9 +49,11 @@ namespace qt {
 // Uniform twiddles of the rows pass.  Indexed only with compile-time constants after unrolling,
 // so they are consumed as constant-bank operands of IMAD (no load instruction).
 __constant__ TwPair c_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
+__constant__ double c_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];  // FP64-quotient companions (LAZY sets; qt_tables.h: dq_companion)
 #endif
 #if !defined(__CUDA_ARCH__)
 extern TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];  // host mirror (table upload / emulation)
+extern double h_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];
 #endif
 
 template <int SET, int KIND> QT_HD TwPair uni_tw(int k) {
@@ -57,6 +61,14 @@ template <int SET, int KIND> QT_HD TwPair uni_tw(int k) {
     return c_uni[SET][KIND][k];
 #else
     return h_uni[SET][KIND][k];
+#endif
+}
+
+template <int SET, int KIND> QT_HD double uni_W(int k) {
+#if defined(__CUDA_ARCH__)
+    return c_uniW[SET][KIND][k];
+#else
+    return h_uniW[SET][KIND][k];
 #endif
 }
 
@@ -383,6 +395,163 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
          ...);
     }
 
+    // ---- FP64-quotient ("DQ") arithmetic for the signed-lazy sets ------------------------------------------------
+    // The Shoup butterfly above keeps the multiply pipe busy for 8 clocks per warp, 4 of them for the mul.hi that
+    // estimates the quotient floor(y w / q).  B200's FP64 pipe runs beside the integer multiply-add at the same rate
+    // (64 lanes/clk/SM each, profiles/ubench_r01s.json), so here the quotient comes from ONE DFMA:
+    //     t = fma(D(y), W, 1.5 * 2^-22),   W = (w / q) 2^1000 (qt_tables.h: dq_companion),
+    // where D(y) is the double whose BIT PATTERN is {lo = y, hi = 0}: the denormal y 2^-1074, no conversion instruction.
+    // y 2^-1074 W is exact inside the FMA, the sum is rounded once to a multiple of 2^-74 = one unit of the low mantissa
+    // word, so that word is rint(y w / q) for any 32-bit UNSIGNED y (|w/q| <= 1/2; the rounding of W moves the product
+    // by < 2^-21) and   y w - rint(y w / q) q   lies in [-q/2 - 1, q/2 + 1].  Butterfly = DFMA + 2 mad.lo + 1 add:
+    // 4 clocks of the multiply pipe, 2 of the FP64 pipe (tools/dq_ubench.cu: exactness on 2^24 random triples, rates).
+    //  * unsigned y: every value v travels in OFFSET FORM v + DQ_OFF, DQ_OFF a multiple of q around 2^30: the same
+    //    residue, never negative.  A butterfly keeps the form by itself (x' = y w + x - qe q inherits x's offset,
+    //    y' = 2x - x' too); only additions of two values and the very first level have to mind it.
+    //  * a value lives in a 64-bit register PAIR whose high half stays 0 (uint64_t, `setlo` replaces the low half), so
+    //    the DFMA reads it where it lies; the high halves come from 32 separate loads of a zero word — were they known
+    //    constants, ptxas would re-create them with a MOV per butterfly.
+    // Ranges (true values): forward |v| < q + LOGN (q/2 + 1); inverse < 2^LB2 q + LB1 (q/2 + 1); both < 40 q.
+    static constexpr uint32_t DQ_OFF = 128u * Q;
+    static_assert(!LAZY || ((128ull + 40) * Q < (1ull << 32) && (1u << LB2) + (LB1 + 1) / 2 + 1 < 40 && 1 + (LOGN + 1) / 2 < 40), "DQ offset form");
+    static QT_HD uint32_t dq_quot(uint64_t y, double W) {
+        const double M = 3.5762786865234375e-07;  // 1.5 * 2^-22
+#if defined(__CUDA_ARCH__)
+        return (uint32_t)__double2loint(fma(__longlong_as_double((long long)y), W, M));
+#else
+        double d;
+        memcpy(&d, &y, sizeof d);
+        const double t = std::fma(d, W, M);
+        uint64_t b;
+        memcpy(&b, &t, sizeof b);
+        return (uint32_t)b;
+#endif
+    }
+    static QT_HD void setlo(uint64_t& v, uint32_t lo) { v = (v & 0xFFFFFFFF00000000ull) | lo; }
+    // (x, y) -> (x + w y, x - w y); x in offset form or not (the outputs inherit it), y any unsigned representative
+    static QT_HD void ct_dq(uint64_t& X, uint64_t& Y, uint32_t w, double W) {
+        const uint32_t x = (uint32_t)X, y = (uint32_t)Y;
+        const uint32_t qe = dq_quot(Y, W);
+        const uint32_t u = y * w + x;
+        const uint32_t xn = u - qe * Q;
+#ifndef QT_DQ_SWAP
+#define QT_DQ_SWAP 1
+#endif
+        if (QT_DQ_SWAP) {  // x' goes into y's pair (y is dead), y' = 2x - x' over x: no copy of a high half
+            const uint64_t ox = X;
+            X = Y;
+            Y = ox;
+        }
+        setlo(X, xn);
+        setlo(Y, x + x - xn);
+    }
+    // The same quotient for a 32-bit two's-complement value of the Shoup kernels (|y| < 40 q): the offset is added on the
+    // way into the staging pair, the product uses the staged value too (same residue), and the result is a signed-lazy
+    // value again (|y w - qe q| <= q/2 + 1, tighter than Shoup's [-q/2, 3q/2)) — so single butterflies of the Shoup
+    // kernels can take this form: QT_DQ_UNI = k sends every k-th butterfly with a UNIFORM twiddle (constant-bank W)
+    // through the FP64 pipe, moving 4 multiply-pipe clocks per such butterfly to the FP64 pipe and the ALU.
+#ifndef QT_DQ_UNI
+#define QT_DQ_UNI 0
+#endif
+    static QT_HD void ct_dq32(uint32_t& x, uint32_t& y, uint32_t w, double W) {
+        const uint32_t ys = y + DQ_OFF;
+        const uint32_t qe = dq_quot((uint64_t)ys, W);
+        const uint32_t xn = ys * w + x - qe * Q;
+        y = x + x - xn;
+        x = xn;
+    }
+    template <int KIND> static QT_HD void ct_uni(uint32_t& x, uint32_t& y, uint32_t k, uint32_t idx) {
+        if (LAZY && QT_DQ_UNI != 0 && idx % (QT_DQ_UNI ? QT_DQ_UNI : 1) == 0) ct_dq32(x, y, uni_tw<SET, KIND>(k).w, uni_W<SET, KIND>(k));
+        else ct(x, y, uni_tw<SET, KIND>(k), idx);
+    }
+    struct TwDQ { uint32_t w; double W; };
+    static QT_HD TwDQ lane_slot_dq(const TwQuad* tw, const TwW2* twW, uint32_t slot, uint32_t stride) {
+        const TwQuad qd = tw[(size_t)(slot >> 1) * stride];
+        const TwW2 wd = twW[(size_t)(slot >> 1) * stride];
+        return (slot & 1) ? TwDQ{qd.w1, wd.W1} : TwDQ{qd.w0, wd.W0};
+    }
+    struct LanePtrsW { const TwW2 *fwd, *inv, *scale; };
+    static QT_HD LanePtrsW lane_ptrs_w(const TwW2* tab, uint32_t lane) {
+        return LanePtrsW{tab + lane % BLOCKS, tab + TW_QUADS + lane % LPP, tab + TW_QUADS + INV_QUADS + lane % LPP};
+    }
+    // forward, rows layout; input: canonical coefficients in the low halves (NOT in offset form)
+    static QT_HD void fwd_rows_dq(uint64_t (&v)[E]) {
+#pragma unroll
+        for (uint32_t r = 0; r < E / 2; r++) setlo(v[r], (uint32_t)v[r] + DQ_OFF);  // the x inputs of level 0 carry the offset in
+#pragma unroll
+        for (uint32_t l = 0; l < LB1; l++) {
+            const uint32_t half = E >> (l + 1);
+#pragma unroll
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t g = i / half, j = i % half;
+                ct_dq(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>((1u << l) + g).w, uni_W<SET, UNI_FWD>((1u << l) + g));
+            }
+        }
+    }
+    static QT_HD void fwd_cols_dq(uint64_t (&v)[E], const TwQuad* tw, const TwW2* twW) {
+#pragma unroll
+        for (uint32_t k = 0; k < LB2; k++) {
+            const uint32_t half = (E >> 1) >> (k + LB1 + LOGE - LOGN);
+            const uint32_t G = E / (2 * half);
+#pragma unroll
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t g = i / half, j = i % half;
+                const TwDQ t = lane_slot_dq(tw, twW, G - G0 + g, BLOCKS);
+                ct_dq(v[2 * g * half + j], v[2 * g * half + j + half], t.w, t.W);
+            }
+        }
+    }
+    // NTT-domain product with the stashed first operand (both in offset form): a b 2^-32, offset form
+    static QT_HD void pointwise_dq_stash(uint64_t (&a)[E], const uint32_t* stash, uint32_t lane) {
+#pragma unroll
+        for (uint32_t c = 0; c < E / 4; c++) {
+            const U4 u = *reinterpret_cast<const U4*>(stash + swz(E * lane + 4 * c));
+            setlo(a[4 * c], smul_mont((uint32_t)a[4 * c] - DQ_OFF, u.x - DQ_OFF) + DQ_OFF);
+            setlo(a[4 * c + 1], smul_mont((uint32_t)a[4 * c + 1] - DQ_OFF, u.y - DQ_OFF) + DQ_OFF);
+            setlo(a[4 * c + 2], smul_mont((uint32_t)a[4 * c + 2] - DQ_OFF, u.z - DQ_OFF) + DQ_OFF);
+            setlo(a[4 * c + 3], smul_mont((uint32_t)a[4 * c + 3] - DQ_OFF, u.w - DQ_OFF) + DQ_OFF);
+        }
+    }
+    // inverse, cols layout: cyclic decimation-in-time (see inv_cols); the multiplication-free butterflies re-centre the offset
+    static QT_HD void inv_cols_dq(uint64_t (&v)[E]) {
+#pragma unroll
+        for (uint32_t s_ = 0; s_ < LB2; s_++) {
+            const uint32_t l = 1u << s_;
+#pragma unroll
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t u = i / l, j = i % l;
+                uint64_t& x = v[2 * l * u + j];
+                uint64_t& y = v[2 * l * u + j + l];
+                if (j == 0) {
+                    const uint32_t a = (uint32_t)x, b = (uint32_t)y;
+                    setlo(x, a + b - DQ_OFF);
+                    setlo(y, a - b + DQ_OFF);
+                } else {
+                    ct_dq(x, y, uni_tw<SET, UNI_INV_PLAIN>(l + j).w, uni_W<SET, UNI_INV_PLAIN>(l + j));
+                }
+            }
+        }
+    }
+    // inverse, rows layout, and the output scale; out canonical in [0, q)
+    static QT_HD void inv_rows_dq(uint64_t (&v)[E], uint32_t (&out)[E], const LanePtrs& p, const LanePtrsW& pw) {
+#pragma unroll
+        for (uint32_t k = 0; k < LB1; k++) {
+            const uint32_t G = 1u << k;
+#pragma unroll
+            for (uint32_t i = 0; i < E / 2; i++) {
+                const uint32_t u = i / G, g = i % G;
+                const TwDQ t = lane_slot_dq(p.inv, pw.inv, G - 1 + g, LPP);
+                ct_dq(v[2 * G * u + g], v[2 * G * u + g + G], t.w, t.W);
+            }
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < E; r++) {
+            const TwDQ t = lane_slot_dq(p.scale, pw.scale, r, LPP);
+            const uint32_t m = (uint32_t)v[r] * t.w - dq_quot(v[r], t.W) * Q;  // [-q/2 - 1, q/2 + 1]
+            out[r] = umin32(m, m + Q);
+        }
+    }
+
     // ---- transforms on one lane's registers ---------------------------------------------------
     // rows layout, forward levels 0..LB1-1 (register distance E/2 .. 1)
     // ub: offset into the uniform tables (split tiles: 32 * half, a run-time value; otherwise 0 and
@@ -398,7 +567,8 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {  // flat butterfly index: constant trip count
                 const uint32_t g = i / half, j = i % half;
-                ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>(ub + (1u << l) + g), i);
+                if (LAZY && QT_DQ_UNI) ct_uni<UNI_FWD>(v[2 * g * half + j], v[2 * g * half + j + half], ub + (1u << l) + g, i + l);
+                else ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>(ub + (1u << l) + g), i);
             }
         }
     }
@@ -451,6 +621,8 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
                         const uint32_t a = x, b = y;
                         x = a + b;
                         y = a - b;
+                    } else if (QT_DQ_UNI) {
+                        ct_uni<UNI_INV_PLAIN>(x, y, l + j, i + s_);
                     } else {
                         ct(x, y, uni_tw<SET, UNI_INV_PLAIN>(l + j), i);
                     }

@@ -42,8 +42,8 @@ def rand_pair(q, words, seed):
 
 
 # 0 = automatic, 1 = direct coalesced loads, 2 = TMA bulk copies + mbarrier, 3 = n=2048 as two halves (one warp),
-# 4 = n=2048 as two halves by a pair of warps
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+# 4 = n=2048 as two halves by a pair of warps, 5 = FP64-quotient butterflies (the 23-bit moduli: sets 0 and 1)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("s", ALL_SETS)
 @pytest.mark.parametrize("B", [1, 2, 3, 67, 1000, 5001])
 def test_fused_polymul_equals_oracle(engines, oracle, s, B, variant):
@@ -51,6 +51,10 @@ def test_fused_polymul_equals_oracle(engines, oracle, s, B, variant):
     if variant in (3, 4) and s != 3:
         with pytest.raises(Exception):
             eng.set_fused_variant(variant)   # the split tile exists for n=2048 only
+        return
+    if variant == 5 and s not in (0, 1):
+        with pytest.raises(Exception):
+            eng.set_fused_variant(variant)   # FP64-quotient butterflies exist for the signed-lazy sets only
         return
     eng.set_fused_variant(variant)
     try:
