@@ -30,6 +30,8 @@ def emu():
     L.qtemu_nussbaumer_recursive.argtypes = [C.c_int, u, u, u, C.c_size_t]
     L.qtemu_inner_lazy.argtypes = [C.c_int, u, u, u, C.c_size_t]
     L.qtemu_row_f64.argtypes = [C.c_int, u, u, u, C.c_size_t]
+    L.qtemu_polymul_dq.argtypes = [C.c_int, u, u, u, C.c_size_t, C.POINTER(C.c_double)]
+    L.qtemu_dq_remainder.argtypes = [C.c_int, u, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_size_t]
     return L
 
 
@@ -210,3 +212,43 @@ def test_harvey_range_plan_of_p_I(emu):
     assert (fwd, pw, fout_max) == (64, 32, 4)      # forward: 5 free levels, 32 + 32 corrections; one correction per pointwise pair
     assert inv == 84 and rows_out == 11
     assert 2 * fwd + pw + inv + 32 == 276          # + the 32 final subtractions that make the output canonical
+
+
+@pytest.mark.parametrize("s", [SET_I, SET_III])
+def test_fp64_quotient_remainder(emu, oracle, s):
+    """the FP64-quotient product of the DQ butterflies (Tile::dq_quot: one fma on the DENORMAL double whose bit pattern is
+    {y, 0}): for every 32-bit unsigned y and every centred twiddle w, y w - qe q is congruent to y w and lies within
+    q/2 + 1 of zero — what Tile::ct_dq and the range statement in qt_tile.cuh rest on"""
+    q = oracle.params(s).q
+    rng = np.random.default_rng(50 + s)
+    n = 1 << 18
+    y = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    w = rng.integers(-(q // 2), q // 2 + 1, n, dtype=np.int64).astype(np.int32)
+    y[:8] = [0, 1, q - 1, q, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF]
+    w[:8] = [q // 2, -(q // 2), q // 2, -(q // 2), q // 2, -(q // 2), 1, -1]
+    out = np.zeros(n, dtype=np.int32)
+    assert emu.qtemu_dq_remainder(s, _p(y), w.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data_as(C.POINTER(C.c_int32)), n) == 0
+    r = out.astype(np.int64)
+    assert np.abs(r).max() <= q // 2 + 1
+    assert np.array_equal(r % q, (y.astype(object) * w.astype(object) % q).astype(np.int64))
+
+
+@pytest.mark.parametrize("s", [SET_I, SET_III])
+def test_emulated_fp64_quotient_kernel_equals_oracle(emu, oracle, s):
+    """k_polymul_dq (fused variant 5) lane by lane: bit-exact with the oracle, the high half of every register pair stays
+    zero, and no value leaves the +-40 q window the offset form is built for (worst-case operands included)"""
+    p = oracle.params(s)
+    B = 5
+    rng = np.random.default_rng(60 + s)
+    x = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    y = rng.integers(0, p.q, B * p.n, dtype=np.uint32)
+    x[: p.n] = p.q - 1
+    y[: p.n] = p.q - 1
+    x[p.n: 2 * p.n] = 0
+    x[2 * p.n: 3 * p.n] = np.where(np.arange(p.n) % 2 == 0, p.q - 1, 0)
+    z = np.zeros_like(x)
+    stats = (C.c_double * 1)()
+    assert emu.qtemu_polymul_dq(s, _p(x), _p(y), _p(z), B, stats) == 0
+    assert np.array_equal(z, oracle.polymul(s, x, y))
+    assert stats[0] < 40.0
+    assert emu.qtemu_polymul_dq(SET_P_I, _p(x), _p(y), _p(z), B, stats) == -4   # the Harvey sets have no such kernel
