@@ -23,6 +23,7 @@
 namespace qt {
 TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
 double h_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];
+uint32_t h_uniU[NUM_SETS][UNI_KINDS][UNI_MAX];
 }
 
 using namespace qt;
@@ -54,7 +55,8 @@ struct qt_ctx {
     int grid_fused = 0, grid_fwd = 0, grid_inv = 0, grid_nuss = 0, grid_tma = 0;
     int occ_fused = 0, occ_tma = 0, tma_warps = 0;
     TwQuad* d_tab_split = nullptr;          // n=2048 only: tables of the split tile (k_polymul_split)
-    TwW2* d_tabW = nullptr;                 // signed-lazy sets: FP64-quotient companions of d_tab[1] (k_polymul_dq)
+    TwW2* d_tabW = nullptr;                 // signed-lazy sets: the twiddles of d_tab[1] as w / q and as w in [0, q) (k_polymul_dq)
+    TwU2* d_tabU = nullptr;
     bool dq_ok = false;
     bool split_ok = false;
     bool pair_ok = false;                   // n=2048 only: two warps per polynomial (k_polymul_pair)
@@ -140,7 +142,7 @@ template <int SET> int setup_set(qt_ctx* c, const HostTables& T) {
     c->grid_tma = c->occ_tma * c->num_sms;
     if constexpr (Cfg<SET>::LAZY) {
         int o3 = 0;
-        if (c->d_tabW && cudaFuncSetAttribute(k_polymul_dq<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqShape<SET>::SMEM) == cudaSuccess &&
+        if (c->d_tabW && c->d_tabU && cudaFuncSetAttribute(k_polymul_dq<SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqShape<SET>::SMEM) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_polymul_dq<SET>, DqShape<SET>::WARPS * 32, DqShape<SET>::SMEM) == cudaSuccess)
             c->dq_ok = o3 > 0;
         else
@@ -174,14 +176,19 @@ int upload_tables(qt_ctx* c) {
         const size_t bytes = T.blockW[1].size() * sizeof(TwW2);
         QT_CUDA(cudaMalloc(&c->d_tabW, bytes));
         QT_CUDA(cudaMemcpy(c->d_tabW, T.blockW[1].data(), bytes, cudaMemcpyHostToDevice));
+        const size_t bytes_u = T.blockU[1].size() * sizeof(TwU2);
+        QT_CUDA(cudaMalloc(&c->d_tabU, bytes_u));
+        QT_CUDA(cudaMemcpy(c->d_tabU, T.blockU[1].data(), bytes_u, cudaMemcpyHostToDevice));
     }
     {
         std::lock_guard<std::mutex> lk(g_uni_mutex);
         memcpy(h_uni[c->set], T.uni, sizeof(T.uni));
         memcpy(h_uniW[c->set], T.uniW, sizeof(T.uniW));
+        memcpy(h_uniU[c->set], T.uniU, sizeof(T.uniU));
         if (c->device >= 64 || !g_uni_uploaded[c->device][c->set]) {
             QT_CUDA(cudaMemcpyToSymbol(c_uni, T.uni, sizeof(T.uni), (size_t)c->set * sizeof(T.uni)));
             QT_CUDA(cudaMemcpyToSymbol(c_uniW, T.uniW, sizeof(T.uniW), (size_t)c->set * sizeof(T.uniW)));
+            QT_CUDA(cudaMemcpyToSymbol(c_uniU, T.uniU, sizeof(T.uniU), (size_t)c->set * sizeof(T.uniU)));
             if (c->device < 64) g_uni_uploaded[c->device][c->set] = true;
         }
     }
@@ -305,7 +312,7 @@ template <int SET> int launch_polymul(qt_ctx* c, const uint32_t* x, const uint32
     } else if (Cfg<SET>::LAZY && c->dq_ok && aligned && (c->variant == 5 || (c->variant == 0 && QT_AUTO_PREFERS_DQ))) {
         if constexpr (Cfg<SET>::LAZY) {
             const StageGeom g = stage_geom(c, tiles, DqShape<SET>::WARPS, DqShape<SET>::TABLE_BYTES, DqShape<SET>::WARP_BYTES);
-            cudaError_t e = launch_pdl(c, known, k_polymul_dq<SET>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tab[1], c->d_tabW);
+            cudaError_t e = launch_pdl(c, known, k_polymul_dq<SET>, g.grid, g.warps * 32, g.smem, s, x, y, z, B, c->d_tabU, c->d_tabW);
             if (e != cudaSuccess) return (int)e;
         }
     } else if (tma) {
@@ -597,6 +604,7 @@ int qt_destroy(qt_ctx* c) {
         if (c->d_tab[k]) cudaFree(c->d_tab[k]);
     if (c->d_tab_split) cudaFree(c->d_tab_split);
     if (c->d_tabW) cudaFree(c->d_tabW);
+    if (c->d_tabU) cudaFree(c->d_tabU);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;

@@ -303,8 +303,9 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
 
 // ---- FP64-quotient variant of the fused kernel (signed-lazy sets: qTESLA-I, qTESLA-III) ----------------------------
 // Same staging, same buffers, same transposition pattern as k_polymul_tma; the butterflies take their quotient estimate
-// from the FP64 pipe (Tile::ct_dq) instead of a mul.hi, which halves the multiply-pipe time of a product.  Values
-// are 64-bit register pairs with a zero high half (see qt_tile.cuh); the table block is followed by its TwW2 companion.
+// from the FP64 pipe (Tile::ct_dq) instead of a mul.hi, which halves the multiply-pipe time of a product.  Values are
+// register pairs whose high half is the zero high half of an FP64 result (qt_tile.cuh); the table block holds the
+// twiddles as w in [0, q) (TwU2) and w / q (TwW2).
 #ifndef QT_DQ_WARPS
 #define QT_DQ_WARPS 16
 #endif
@@ -312,24 +313,25 @@ template <int SET> struct DqShape {
     using T = Tile<SET>;
     using G = StageShape<SET>;
     static constexpr int WARPS = QT_DQ_WARPS;
-    static constexpr size_t TWW_BYTES = KernelShape<SET>::TW_QUADS * sizeof(TwW2);
-    static constexpr size_t TABLE_BYTES = KernelShape<SET>::TW_BYTES + TWW_BYTES;
+    static constexpr size_t QUADS = KernelShape<SET>::TW_QUADS;
+    static constexpr size_t TABLE_BYTES = QUADS * (sizeof(TwW2) + sizeof(TwU2));
     static constexpr size_t WARP_BYTES = 2 * G::WORDS * sizeof(uint32_t) + 2 * sizeof(uint64_t);
     static constexpr size_t SMEM = TABLE_BYTES + (size_t)WARPS * WARP_BYTES;
 };
 
 template <int SET>
 __global__ void __launch_bounds__(DqShape<SET>::WARPS * 32, 1)
-k_polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwQuad* __restrict__ g_lane, const TwW2* __restrict__ g_laneW) {
+k_polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const TwU2* __restrict__ g_laneU, const TwW2* __restrict__ g_laneW) {
     using T = Tile<SET>;
-    using S = KernelShape<SET>;
+    using D = DqShape<SET>;
     using G = StageShape<SET>;
+    using P64 = typename T::P64;
     static_assert(T::LAZY && QT_TMA_STORE == 0, "FP64-quotient kernel: signed-lazy sets");
     extern __shared__ uint4 smem_raw[];
-    __shared__ uint32_t s_zero[T::E];
-    TwQuad* s_tw = reinterpret_cast<TwQuad*>(smem_raw);
-    TwW2* s_twW = reinterpret_cast<TwW2*>(s_tw + S::TW_QUADS);
-    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_twW + S::TW_QUADS);
+    __shared__ double s_tiny;  // the denormal 2^-1074: the seeds of the register pairs are products with it
+    TwW2* s_twW = reinterpret_cast<TwW2*>(smem_raw);
+    TwU2* s_twU = reinterpret_cast<TwU2*>(s_twW + D::QUADS);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_twU + D::QUADS);
     const int NW = (int)(blockDim.x >> 5);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
 
@@ -361,9 +363,15 @@ k_polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
-    if (threadIdx.x < T::E) s_zero[threadIdx.x] = 0u;
-    copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
-    copy_table_to_smem(reinterpret_cast<TwQuad*>(s_twW), reinterpret_cast<const TwQuad*>(g_laneW), S::TW_QUADS);
+    if (threadIdx.x == 0) s_tiny = __longlong_as_double(1ll);
+    {
+        const uint4* sw = reinterpret_cast<const uint4*>(g_laneW);
+        uint4* dw = reinterpret_cast<uint4*>(s_twW);
+        for (size_t i = threadIdx.x; i < D::QUADS; i += blockDim.x) dw[i] = __ldg(sw + i);
+        const uint2* su = reinterpret_cast<const uint2*>(g_laneU);
+        uint2* du = reinterpret_cast<uint2*>(s_twU);
+        for (size_t i = threadIdx.x; i < D::QUADS; i += blockDim.x) du[i] = __ldg(su + i);
+    }
     pdl_wait();
     if (lane == 0 && tile < ntiles) {
         issue(x, A, bar_a, tile);
@@ -371,41 +379,50 @@ k_polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, co
     }
     __syncthreads();
 
-    const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
-    const typename T::LanePtrsW PW = T::lane_ptrs_w(s_twW, lane);
-    // a value = (zero high half loaded from s_zero) : (low half); re-made whenever the low halves are loaded, so that no
-    // register pair is carried around a loop (qt_tile.cuh)
-#define QT_DQ_PAIR(r, lo) ((((uint64_t) * (volatile uint32_t*)&s_zero[r]) << 32) | (uint64_t)(lo))  /* volatile: one LDS each, never a 128-bit load into four consecutive registers */
+    const typename T::LanePtrsDQ P = T::lane_ptrs_dq(s_twU, s_twW, lane);
+    // seed of register r: the (zero) high half of an FP64 product made here and now — a volatile operand keeps the
+    // compiler from hoisting the sixteen products of a pass out of the loops and copying their results into place
+#define QT_DQ_SEED(r) (P64{tiny * uni_W<SET, UNI_FWD>(r)})
     uint32_t phase = 0;
     for (; tile < ntiles; tile += stride, phase ^= 1) {
         const size_t base = tile * T::C::TILE_WORDS;
         const bool valid = tile * T::PPW + lane / T::LPP < batch;
         const bool more = tile + stride < ntiles;
-        uint64_t v[T::E];
+        P64 v[T::E];
 #pragma unroll 1
         for (int op = 0; op < 2; op++) {  // one copy of the forward-transform code for x and y
             uint32_t* st = op ? B : A;
             mbar_wait(op ? bar_b : bar_a, phase);
+            {
+                const double tiny = *(volatile double*)&s_tiny;
 #pragma unroll
-            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, st[G::off(lane, r)]);
+                for (uint32_t r = 0; r < T::E; r++) {
+                    v[r] = (QT_DQ_SWAP || r >= T::E / 2) ? QT_DQ_SEED(r).with_lo(st[G::off(lane, r)]) : P64::make(st[G::off(lane, r)], 0u);
+                }
+            }
             __syncwarp();
             T::fwd_rows_dq(v);
             if (T::PPW == 2) {
                 const typename T::RowBases RB = T::row_bases(lane);
 #pragma unroll
-                for (uint32_t r = 0; r < T::E; r++) st[T::rows_addr(RB, r)] = (uint32_t)v[r];
+                for (uint32_t r = 0; r < T::E; r++) st[T::rows_addr(RB, r)] = v[r].lo();
             } else {
 #pragma unroll
-                for (uint32_t r = 0; r < T::E; r++) st[T::swz(T::row_off(lane, r))] = (uint32_t)v[r];
+                for (uint32_t r = 0; r < T::E; r++) st[T::swz(T::row_off(lane, r))] = v[r].lo();
             }
             __syncwarp();
+            {
+                const double tiny = *(volatile double*)&s_tiny;
 #pragma unroll
-            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, st[T::swz(T::E * lane + r)]);
-            T::fwd_cols_dq(v, P.fwd, PW.fwd);
+                for (uint32_t r = 0; r < T::E; r++) {
+                    v[r] = (QT_DQ_SWAP || T::dq_cols_first_y(r)) ? QT_DQ_SEED(r).with_lo(st[T::swz(T::E * lane + r)]) : P64::make(st[T::swz(T::E * lane + r)], 0u);
+                }
+            }
+            T::fwd_cols_dq(v, P);
             if (op == 0) {
                 __syncwarp();             // every lane has read its columns before A is overwritten
 #pragma unroll
-                for (uint32_t r = 0; r < T::E; r++) A[T::swz(T::E * lane + r)] = (uint32_t)v[r];  // stash NTT(x); each lane reads back only what it wrote
+                for (uint32_t r = 0; r < T::E; r++) A[T::swz(T::E * lane + r)] = v[r].lo();  // stash NTT(x); each lane reads back only what it wrote
             }
         }
         T::pointwise_dq_stash(v, A, lane);
@@ -414,24 +431,30 @@ k_polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, co
         if (more && lane == 0) issue(x, A, bar_a, tile + stride);
         T::inv_cols_dq(v);
 #pragma unroll
-        for (uint32_t r = 0; r < T::E; r++) B[T::swz(T::E * lane + r)] = (uint32_t)v[r];
+        for (uint32_t r = 0; r < T::E; r++) B[T::swz(T::E * lane + r)] = v[r].lo();
         __syncwarp();
-        if (T::PPW == 2) {
-            const typename T::RowBases RB = T::row_bases(lane);
+        {
+            const double tiny = *(volatile double*)&s_tiny;
+            uint32_t ld[T::E];
+            if (T::PPW == 2) {
+                const typename T::RowBases RB = T::row_bases(lane);
 #pragma unroll
-            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, B[T::rows_addr(RB, r)]);
-        } else {
+                for (uint32_t r = 0; r < T::E; r++) ld[r] = B[T::rows_addr(RB, r)];
+            } else {
 #pragma unroll
-            for (uint32_t r = 0; r < T::E; r++) v[r] = QT_DQ_PAIR(r, B[T::swz(T::row_off(lane, r))]);
+                for (uint32_t r = 0; r < T::E; r++) ld[r] = B[T::swz(T::row_off(lane, r))];
+            }
+#pragma unroll
+            for (uint32_t r = 0; r < T::E; r++) v[r] = (QT_DQ_SWAP || T::dq_rows_first_y(r)) ? QT_DQ_SEED(r).with_lo(ld[r]) : P64::make(ld[r], 0u);
         }
         fence_proxy_async();
         __syncwarp();                     // B is free: fetch the next tile's y into it
         if (more && lane == 0) issue(y, B, bar_b, tile + stride);
         uint32_t out[T::E];
-        T::inv_rows_dq(v, out, P, PW);
+        T::inv_rows_dq(v, out, P);
         T::store_rows(out, z + base, lane, valid);
     }
-#undef QT_DQ_PAIR
+#undef QT_DQ_SEED
 }
 
 // Fused product for n = 2048 (qTESLA-p-III) on the SPLIT tile: a polynomial is two 1024-point halves

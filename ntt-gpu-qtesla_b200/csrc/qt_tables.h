@@ -17,11 +17,13 @@ namespace qt {
 struct alignas(8) TwPair { uint32_t w, ws; };           // twiddle and floor(w * 2^32 / q)
 struct alignas(16) TwQuad { uint32_t w0, ws0, w1, ws1; };  // two consecutive slots (one 128-bit load)
 
-// FP64-quotient companion of a twiddle (qt_tile.cuh, "DQ" butterflies): W = (w centred) / q * 2^1000, so that
-// fma(D(y), W, 1.5 * 2^-22) — D(y) the DENORMAL double whose bit pattern is {lo = y, hi = 0} = y * 2^-1074 — has
-// rint(y w / q) in the low word of its bit pattern.  Two consecutive slots per 128-bit load, like TwQuad.
+// Twiddles of the FP64-quotient ("DQ") butterflies (qt_tile.cuh): w as a representative in [0, q) and W = w / q as a
+// double — D(y) * W, with D(y) the DENORMAL double whose bit pattern is {lo = y, hi = 0}, has the bit pattern
+// {rint(y w / q), 0}.  Two consecutive slots per access, like TwQuad.
 struct alignas(16) TwW2 { double W0, W1; };
-inline double dq_companion(uint32_t w_centred, uint32_t q) { return std::ldexp((double)(int32_t)w_centred / (double)q, 1000); }
+struct alignas(8) TwU2 { uint32_t w0, w1; };
+inline uint32_t dq_unsigned(uint32_t w_centred, uint32_t q) { return (int32_t)w_centred < 0 ? w_centred + q : w_centred; }
+inline double dq_companion(uint32_t w_unsigned, uint32_t q) { return (double)w_unsigned / (double)q; }
 
 enum : int { UNI_FWD = 0, UNI_INV_PLAIN = 1, UNI_INV_FUSED = 2, UNI_KINDS = 3 };
 constexpr int UNI_MAX = 64;  // 2^LB1 for the largest tile (n=2048: 6 strided levels)
@@ -38,9 +40,11 @@ struct HostTables {
     // kernel table blocks (one per output-scale kind): [fwd per-lane][LAZY: inverse per-lane][LAZY: scale]
     std::vector<TwQuad> block[2];  // 0: plain scale n^-1 psi^-i (unfused inverse), 1: fused scale (x 2^32)
     uint32_t fwd_quads, inv_quads, scale_quads;
-    // LAZY sets: the FP64-quotient companions of uni[][] and of block[][] (same indexing)
+    // LAZY sets: the same twiddles for the FP64-quotient kernels (same indexing as uni[][] / block[][])
     double uniW[UNI_KINDS][UNI_MAX];
+    uint32_t uniU[UNI_KINDS][UNI_MAX];
     std::vector<TwW2> blockW[2];
+    std::vector<TwU2> blockU[2];
 };
 
 // LAZY sets store twiddles for the SIGNED Shoup product: w centred in (-q/2, q/2] as a two's-complement word,
@@ -152,12 +156,19 @@ inline void build_tables(int set, HostTables* T) {
             }
     }
     for (int kind = 0; kind < UNI_KINDS; kind++)
-        for (int k = 0; k < UNI_MAX; k++) T->uniW[kind][k] = lazy ? dq_companion(T->uni[kind][k].w, q) : 0.0;
+        for (int k = 0; k < UNI_MAX; k++) {
+            T->uniU[kind][k] = lazy ? dq_unsigned(T->uni[kind][k].w, q) : 0u;
+            T->uniW[kind][k] = lazy ? dq_companion(T->uniU[kind][k], q) : 0.0;
+        }
     for (int kind = 0; kind < 2; kind++) {
         T->blockW[kind].clear();
+        T->blockU[kind].clear();
         if (!lazy) continue;
-        T->blockW[kind].reserve(T->block[kind].size());
-        for (const TwQuad& qd : T->block[kind]) T->blockW[kind].push_back(TwW2{dq_companion(qd.w0, q), dq_companion(qd.w1, q)});
+        for (const TwQuad& qd : T->block[kind]) {
+            const TwU2 u{dq_unsigned(qd.w0, q), dq_unsigned(qd.w1, q)};
+            T->blockU[kind].push_back(u);
+            T->blockW[kind].push_back(TwW2{dq_companion(u.w0, q), dq_companion(u.w1, q)});
+        }
     }
 }
 

@@ -49,11 +49,14 @@ namespace qt {
 // Uniform twiddles of the rows pass.  Indexed only with compile-time constants after unrolling,
 // so they are consumed as constant-bank operands of IMAD (no load instruction).
 __constant__ TwPair c_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
-__constant__ double c_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];  // FP64-quotient companions (LAZY sets; qt_tables.h: dq_companion)
+// uniform twiddles of the FP64-quotient kernels (LAZY sets; qt_tables.h): w in [0, q) and W = w / q
+__constant__ double c_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];
+__constant__ uint32_t c_uniU[NUM_SETS][UNI_KINDS][UNI_MAX];
 #endif
 #if !defined(__CUDA_ARCH__)
 extern TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];  // host mirror (table upload / emulation)
 extern double h_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];
+extern uint32_t h_uniU[NUM_SETS][UNI_KINDS][UNI_MAX];
 #endif
 
 template <int SET, int KIND> QT_HD TwPair uni_tw(int k) {
@@ -69,6 +72,14 @@ template <int SET, int KIND> QT_HD double uni_W(int k) {
     return c_uniW[SET][KIND][k];
 #else
     return h_uniW[SET][KIND][k];
+#endif
+}
+
+template <int SET, int KIND> QT_HD uint32_t uni_U(int k) {
+#if defined(__CUDA_ARCH__)
+    return c_uniU[SET][KIND][k];
+#else
+    return h_uniU[SET][KIND][k];
 #endif
 }
 
@@ -398,97 +409,107 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
     // ---- FP64-quotient ("DQ") arithmetic for the signed-lazy sets ------------------------------------------------
     // The Shoup butterfly above keeps the multiply pipe busy for 8 clocks per warp, 4 of them for the mul.hi that
     // estimates the quotient floor(y w / q).  B200's FP64 pipe runs beside the integer multiply-add at the same rate
-    // (64 lanes/clk/SM each, profiles/ubench_r01s.json), so here the quotient comes from ONE DFMA:
-    //     t = fma(D(y), W, 1.5 * 2^-22),   W = (w / q) 2^1000 (qt_tables.h: dq_companion),
-    // where D(y) is the double whose BIT PATTERN is {lo = y, hi = 0}: the denormal y 2^-1074, no conversion instruction.
-    // y 2^-1074 W is exact inside the FMA, the sum is rounded once to a multiple of 2^-74 = one unit of the low mantissa
-    // word, so that word is rint(y w / q) for any 32-bit UNSIGNED y (|w/q| <= 1/2; the rounding of W moves the product
-    // by < 2^-21) and   y w - rint(y w / q) q   lies in [-q/2 - 1, q/2 + 1].  Butterfly = DFMA + 2 mad.lo + 1 add:
-    // 4 clocks of the multiply pipe, 2 of the FP64 pipe (tools/dq_ubench.cu: exactness on 2^24 random triples, rates).
+    // (64 lanes/clk/SM each, profiles/ubench_r01s.json), so here the quotient comes from ONE FP64 multiplication:
+    //     t = D(y) * (w / q),      D(y) = the double whose BIT PATTERN is {lo = y, hi = 0}: the DENORMAL y 2^-1074.
+    // The product of a denormal and a number below 1 is a denormal again, i.e. it is rounded to a multiple of 2^-1074:
+    // t's bit pattern is {rint(y w / q), 0} — an integer quotient without any conversion instruction, for every
+    // UNSIGNED 32-bit y and twiddle w in [0, q) — and   y w - rint(y w / q) q   lies in [-q/2 - 1, q/2 + 1] (the
+    // rounding of w/q to a double moves the product by < 2^-21).  Butterfly = DMUL + 2 mad.lo + 1 add: 4 clocks of the
+    // multiply pipe and 2 of the FP64 pipe per warp (tools/dq_ubench.cu: exactness and rates).
     //  * unsigned y: every value v travels in OFFSET FORM v + DQ_OFF, DQ_OFF a multiple of q around 2^30: the same
     //    residue, never negative.  A butterfly keeps the form by itself (x' = y w + x - qe q inherits x's offset,
     //    y' = 2x - x' too); only additions of two values and the very first level have to mind it.
-    //  * a value lives in a 64-bit register PAIR whose high half stays 0 (uint64_t, `setlo` replaces the low half), so
-    //    the DFMA reads it where it lies; the high halves come from 32 separate loads of a zero word — were they known
-    //    constants, ptxas would re-create them with a MOV per butterfly.
+    //  * the FP64 unit reads a register PAIR.  A value is a P64 {lo, hi} whose hi is the zero high half of SOME earlier
+    //    FP64 result: x' = mad(qe, -q, u) overwrites qe where the DMUL left it, so {x', hi(t)} is a pair with a zero high
+    //    half by construction, and y' overwrites y in y's own pair.  Only the 16 y operands of a pass's first level
+    //    need a seed (dq_seed).  Were the high halves written as constants, ptxas would re-create them with a MOV per
+    //    butterfly; were they loaded, it copies them around.
     // Ranges (true values): forward |v| < q + LOGN (q/2 + 1); inverse < 2^LB2 q + LB1 (q/2 + 1); both < 40 q.
     static constexpr uint32_t DQ_OFF = 128u * Q;
     static_assert(!LAZY || ((128ull + 40) * Q < (1ull << 32) && (1u << LB2) + (LB1 + 1) / 2 + 1 < 40 && 1 + (LOGN + 1) / 2 < 40), "DQ offset form");
-    static QT_HD uint32_t dq_quot(uint64_t y, double W) {
-        const double M = 3.5762786865234375e-07;  // 1.5 * 2^-22
-#if defined(__CUDA_ARCH__)
-        return (uint32_t)__double2loint(fma(__longlong_as_double((long long)y), W, M));
-#else
+    // A value: the 64-bit register pair as ONE object (a double, so that the FP64 unit reads it where it lies); lo() is a
+    // sub-register read, with_lo() the same pair with the low half replaced.
+    struct P64 {
         double d;
-        memcpy(&d, &y, sizeof d);
-        const double t = std::fma(d, W, M);
-        uint64_t b;
-        memcpy(&b, &t, sizeof b);
-        return (uint32_t)b;
+        QT_HD uint32_t lo() const {
+#if defined(__CUDA_ARCH__)
+            return (uint32_t)__double2loint(d);
+#else
+            uint64_t b; memcpy(&b, &d, sizeof b); return (uint32_t)b;
 #endif
-    }
-    static QT_HD void setlo(uint64_t& v, uint32_t lo) { v = (v & 0xFFFFFFFF00000000ull) | lo; }
-    // (x, y) -> (x + w y, x - w y); x in offset form or not (the outputs inherit it), y any unsigned representative
-    static QT_HD void ct_dq(uint64_t& X, uint64_t& Y, uint32_t w, double W) {
-        const uint32_t x = (uint32_t)X, y = (uint32_t)Y;
-        const uint32_t qe = dq_quot(Y, W);
-        const uint32_t u = y * w + x;
-        const uint32_t xn = u - qe * Q;
-#ifndef QT_DQ_SWAP
-#define QT_DQ_SWAP 1
-#endif
-        if (QT_DQ_SWAP) {  // x' goes into y's pair (y is dead), y' = 2x - x' over x: no copy of a high half
-            const uint64_t ox = X;
-            X = Y;
-            Y = ox;
         }
-        setlo(X, xn);
-        setlo(Y, x + x - xn);
-    }
-    // The same quotient for a 32-bit two's-complement value of the Shoup kernels (|y| < 40 q): the offset is added on the
-    // way into the staging pair, the product uses the staged value too (same residue), and the result is a signed-lazy
-    // value again (|y w - qe q| <= q/2 + 1, tighter than Shoup's [-q/2, 3q/2)) — so single butterflies of the Shoup
-    // kernels can take this form: QT_DQ_UNI = k sends every k-th butterfly with a UNIFORM twiddle (constant-bank W)
-    // through the FP64 pipe, moving 4 multiply-pipe clocks per such butterfly to the FP64 pipe and the ALU.
-#ifndef QT_DQ_UNI
-#define QT_DQ_UNI 0
+        QT_HD uint32_t hi() const {
+#if defined(__CUDA_ARCH__)
+            return (uint32_t)__double2hiint(d);
+#else
+            uint64_t b; memcpy(&b, &d, sizeof b); return (uint32_t)(b >> 32);
 #endif
-    static QT_HD void ct_dq32(uint32_t& x, uint32_t& y, uint32_t w, double W) {
-        const uint32_t ys = y + DQ_OFF;
-        const uint32_t qe = dq_quot((uint64_t)ys, W);
-        const uint32_t xn = ys * w + x - qe * Q;
-        y = x + x - xn;
-        x = xn;
+        }
+        QT_HD P64 with_lo(uint32_t v) const { return make(v, hi()); }
+        static QT_HD P64 make(uint32_t lo_, uint32_t hi_) {
+#if defined(__CUDA_ARCH__)
+            return P64{__hiloint2double((int)hi_, (int)lo_)};
+#else
+            const uint64_t b = ((uint64_t)hi_ << 32) | lo_;
+            P64 r; memcpy(&r.d, &b, sizeof b); return r;
+#endif
+        }
+    };
+    // {rint(y W), 0} for W = w / q in [0, 1)
+    static QT_HD P64 dq_quot(P64 y, double W) {
+#if defined(__CUDA_ARCH__) && !defined(QT_DQ_PLAIN_MUL)
+        // fma with a +0 addend, NOT a plain product: given mul.f64 followed by mad.lo(lo(t), -q, u), ptxas 12.9 emitted ONE
+        // DMUL of W with a constant pair {-q, 4} per level and x' = y * lo(that) + u for every butterfly — it moved the integer
+        // multiplication through the FP64 product as if D(y) W were linear in y.  Wrong results for qTESLA-I (run r02B,
+        // tools/dq_ptxas_repro.cu: GPU vs host level by level); the fma form is compiled as written (DFMA Rt, Ry, W, RZ).
+        double t;
+        asm("fma.rn.f64 %0, %1, %2, 0d0000000000000000;" : "=d"(t) : "d"(y.d), "d"(W));
+        return P64{t};
+#else
+        return P64{y.d * W};
+#endif
     }
-    template <int KIND> static QT_HD void ct_uni(uint32_t& x, uint32_t& y, uint32_t k, uint32_t idx) {
-        if (LAZY && QT_DQ_UNI != 0 && idx % (QT_DQ_UNI ? QT_DQ_UNI : 1) == 0) ct_dq32(x, y, uni_tw<SET, KIND>(k).w, uni_W<SET, KIND>(k));
-        else ct(x, y, uni_tw<SET, KIND>(k), idx);
+    // (x, y) -> (x + w y, x - w y); x in offset form or not (the outputs inherit it), y any unsigned representative in a pair
+    static QT_HD void ct_dq(P64& X, P64& Y, uint32_t w, double W) {
+        const P64 t = dq_quot(Y, W);
+        const uint32_t x = X.lo(), y = Y.lo();
+        const uint32_t u = y * w + x;
+        const uint32_t xn = u - t.lo() * Q;
+#ifndef QT_DQ_SWAP
+#define QT_DQ_SWAP 0
+#endif
+        if (QT_DQ_SWAP) Y = X.with_lo(x + x - xn);  // y' over x, in x's pair (every register of a pass then needs a seed)
+        else Y = Y.with_lo(x + x - xn);             // y' over y, in y's pair
+        X = t.with_lo(xn);                          // x' over the quotient, in the pair the FP64 unit wrote
     }
     struct TwDQ { uint32_t w; double W; };
-    static QT_HD TwDQ lane_slot_dq(const TwQuad* tw, const TwW2* twW, uint32_t slot, uint32_t stride) {
-        const TwQuad qd = tw[(size_t)(slot >> 1) * stride];
+    // per-lane tables of the DQ kernel: w in [0, q) and W = w / q, two slots per access
+    static QT_HD TwDQ lane_slot_dq(const TwU2* tw, const TwW2* twW, uint32_t slot, uint32_t stride) {
+        const TwU2 qd = tw[(size_t)(slot >> 1) * stride];
         const TwW2 wd = twW[(size_t)(slot >> 1) * stride];
         return (slot & 1) ? TwDQ{qd.w1, wd.W1} : TwDQ{qd.w0, wd.W0};
     }
-    struct LanePtrsW { const TwW2 *fwd, *inv, *scale; };
-    static QT_HD LanePtrsW lane_ptrs_w(const TwW2* tab, uint32_t lane) {
-        return LanePtrsW{tab + lane % BLOCKS, tab + TW_QUADS + lane % LPP, tab + TW_QUADS + INV_QUADS + lane % LPP};
+    struct LanePtrsDQ { const TwU2 *fwd, *inv, *scale; const TwW2 *fwdW, *invW, *scaleW; };
+    static QT_HD LanePtrsDQ lane_ptrs_dq(const TwU2* tab, const TwW2* tabW, uint32_t lane) {
+        return LanePtrsDQ{tab + lane % BLOCKS, tab + TW_QUADS + lane % LPP, tab + TW_QUADS + INV_QUADS + lane % LPP,
+                          tabW + lane % BLOCKS, tabW + TW_QUADS + lane % LPP, tabW + TW_QUADS + INV_QUADS + lane % LPP};
     }
-    // forward, rows layout; input: canonical coefficients in the low halves (NOT in offset form)
-    static QT_HD void fwd_rows_dq(uint64_t (&v)[E]) {
+    // forward, rows layout; input: canonical coefficients in lo (NOT in offset form); hi of v[E/2 ..] seeded by the caller
+    static QT_HD void fwd_rows_dq(P64 (&v)[E]) {
 #pragma unroll
-        for (uint32_t r = 0; r < E / 2; r++) setlo(v[r], (uint32_t)v[r] + DQ_OFF);  // the x inputs of level 0 carry the offset in
+        for (uint32_t r = 0; r < E / 2; r++) v[r] = v[r].with_lo(v[r].lo() + DQ_OFF);  // the x inputs of level 0 carry the offset in
 #pragma unroll
         for (uint32_t l = 0; l < LB1; l++) {
             const uint32_t half = E >> (l + 1);
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t g = i / half, j = i % half;
-                ct_dq(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>((1u << l) + g).w, uni_W<SET, UNI_FWD>((1u << l) + g));
+                ct_dq(v[2 * g * half + j], v[2 * g * half + j + half], uni_U<SET, UNI_FWD>((1u << l) + g), uni_W<SET, UNI_FWD>((1u << l) + g));
             }
         }
     }
-    static QT_HD void fwd_cols_dq(uint64_t (&v)[E], const TwQuad* tw, const TwW2* twW) {
+    // forward, cols layout; input in offset form; hi of the first level's y operands seeded by the caller
+    static QT_HD void fwd_cols_dq(P64 (&v)[E], const LanePtrsDQ& p) {
 #pragma unroll
         for (uint32_t k = 0; k < LB2; k++) {
             const uint32_t half = (E >> 1) >> (k + LB1 + LOGE - LOGN);
@@ -496,58 +517,62 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t g = i / half, j = i % half;
-                const TwDQ t = lane_slot_dq(tw, twW, G - G0 + g, BLOCKS);
+                const TwDQ t = lane_slot_dq(p.fwd, p.fwdW, G - G0 + g, BLOCKS);
                 ct_dq(v[2 * g * half + j], v[2 * g * half + j + half], t.w, t.W);
             }
         }
     }
+    // y operands of the first level of fwd_cols_dq / of inv_rows_dq: the registers the caller has to seed
+    static QT_CHD bool dq_cols_first_y(uint32_t r) { return ((r / ((E >> 1) >> (LB1 + LOGE - LOGN))) & 1u) != 0; }
+    static QT_CHD bool dq_rows_first_y(uint32_t r) { return (r & 1u) != 0; }
     // NTT-domain product with the stashed first operand (both in offset form): a b 2^-32, offset form
-    static QT_HD void pointwise_dq_stash(uint64_t (&a)[E], const uint32_t* stash, uint32_t lane) {
+    static QT_HD void pointwise_dq_stash(P64 (&a)[E], const uint32_t* stash, uint32_t lane) {
 #pragma unroll
         for (uint32_t c = 0; c < E / 4; c++) {
             const U4 u = *reinterpret_cast<const U4*>(stash + swz(E * lane + 4 * c));
-            setlo(a[4 * c], smul_mont((uint32_t)a[4 * c] - DQ_OFF, u.x - DQ_OFF) + DQ_OFF);
-            setlo(a[4 * c + 1], smul_mont((uint32_t)a[4 * c + 1] - DQ_OFF, u.y - DQ_OFF) + DQ_OFF);
-            setlo(a[4 * c + 2], smul_mont((uint32_t)a[4 * c + 2] - DQ_OFF, u.z - DQ_OFF) + DQ_OFF);
-            setlo(a[4 * c + 3], smul_mont((uint32_t)a[4 * c + 3] - DQ_OFF, u.w - DQ_OFF) + DQ_OFF);
+            a[4 * c] = a[4 * c].with_lo(smul_mont(a[4 * c].lo() - DQ_OFF, u.x - DQ_OFF) + DQ_OFF);
+            a[4 * c + 1] = a[4 * c + 1].with_lo(smul_mont(a[4 * c + 1].lo() - DQ_OFF, u.y - DQ_OFF) + DQ_OFF);
+            a[4 * c + 2] = a[4 * c + 2].with_lo(smul_mont(a[4 * c + 2].lo() - DQ_OFF, u.z - DQ_OFF) + DQ_OFF);
+            a[4 * c + 3] = a[4 * c + 3].with_lo(smul_mont(a[4 * c + 3].lo() - DQ_OFF, u.w - DQ_OFF) + DQ_OFF);
         }
     }
-    // inverse, cols layout: cyclic decimation-in-time (see inv_cols); the multiplication-free butterflies re-centre the offset
-    static QT_HD void inv_cols_dq(uint64_t (&v)[E]) {
+    // inverse, cols layout: cyclic decimation-in-time (see inv_cols); the multiplication-free butterflies re-centre the
+    // offset.  Every register is still in the pair the forward cols pass left it in.
+    static QT_HD void inv_cols_dq(P64 (&v)[E]) {
 #pragma unroll
         for (uint32_t s_ = 0; s_ < LB2; s_++) {
             const uint32_t l = 1u << s_;
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t u = i / l, j = i % l;
-                uint64_t& x = v[2 * l * u + j];
-                uint64_t& y = v[2 * l * u + j + l];
+                P64& x = v[2 * l * u + j];
+                P64& y = v[2 * l * u + j + l];
                 if (j == 0) {
-                    const uint32_t a = (uint32_t)x, b = (uint32_t)y;
-                    setlo(x, a + b - DQ_OFF);
-                    setlo(y, a - b + DQ_OFF);
+                    const uint32_t a = x.lo(), b = y.lo();
+                    x = x.with_lo(a + b - DQ_OFF);
+                    y = y.with_lo(a - b + DQ_OFF);
                 } else {
-                    ct_dq(x, y, uni_tw<SET, UNI_INV_PLAIN>(l + j).w, uni_W<SET, UNI_INV_PLAIN>(l + j));
+                    ct_dq(x, y, uni_U<SET, UNI_INV_PLAIN>(l + j), uni_W<SET, UNI_INV_PLAIN>(l + j));
                 }
             }
         }
     }
-    // inverse, rows layout, and the output scale; out canonical in [0, q)
-    static QT_HD void inv_rows_dq(uint64_t (&v)[E], uint32_t (&out)[E], const LanePtrs& p, const LanePtrsW& pw) {
+    // inverse, rows layout, and the output scale; out canonical in [0, q); hi of the odd registers seeded by the caller
+    static QT_HD void inv_rows_dq(P64 (&v)[E], uint32_t (&out)[E], const LanePtrsDQ& p) {
 #pragma unroll
         for (uint32_t k = 0; k < LB1; k++) {
             const uint32_t G = 1u << k;
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {
                 const uint32_t u = i / G, g = i % G;
-                const TwDQ t = lane_slot_dq(p.inv, pw.inv, G - 1 + g, LPP);
+                const TwDQ t = lane_slot_dq(p.inv, p.invW, G - 1 + g, LPP);
                 ct_dq(v[2 * G * u + g], v[2 * G * u + g + G], t.w, t.W);
             }
         }
 #pragma unroll
         for (uint32_t r = 0; r < E; r++) {
-            const TwDQ t = lane_slot_dq(p.scale, pw.scale, r, LPP);
-            const uint32_t m = (uint32_t)v[r] * t.w - dq_quot(v[r], t.W) * Q;  // [-q/2 - 1, q/2 + 1]
+            const TwDQ t = lane_slot_dq(p.scale, p.scaleW, r, LPP);
+            const uint32_t m = v[r].lo() * t.w - dq_quot(v[r], t.W).lo() * Q;  // [-q/2 - 1, q/2 + 1]
             out[r] = umin32(m, m + Q);
         }
     }
@@ -567,8 +592,7 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
 #pragma unroll
             for (uint32_t i = 0; i < E / 2; i++) {  // flat butterfly index: constant trip count
                 const uint32_t g = i / half, j = i % half;
-                if (LAZY && QT_DQ_UNI) ct_uni<UNI_FWD>(v[2 * g * half + j], v[2 * g * half + j + half], ub + (1u << l) + g, i + l);
-                else ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>(ub + (1u << l) + g), i);
+                ct(v[2 * g * half + j], v[2 * g * half + j + half], uni_tw<SET, UNI_FWD>(ub + (1u << l) + g), i);
             }
         }
     }
@@ -621,8 +645,6 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
                         const uint32_t a = x, b = y;
                         x = a + b;
                         y = a - b;
-                    } else if (QT_DQ_UNI) {
-                        ct_uni<UNI_INV_PLAIN>(x, y, l + j, i + s_);
                     } else {
                         ct(x, y, uni_tw<SET, UNI_INV_PLAIN>(l + j), i);
                     }

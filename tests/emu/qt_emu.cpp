@@ -14,6 +14,7 @@
 namespace qt {
 TwPair h_uni[NUM_TILE_SETS][UNI_KINDS][UNI_MAX];
 double h_uniW[NUM_SETS][UNI_KINDS][UNI_MAX];
+uint32_t h_uniU[NUM_SETS][UNI_KINDS][UNI_MAX];
 }
 using namespace qt;
 
@@ -26,23 +27,32 @@ template <int SET> struct Emu {
     Emu() {
         build_tables(SET, &tab);
         memcpy(h_uni[SET], tab.uni, sizeof(tab.uni));
-        if (SET < NUM_SETS) memcpy(h_uniW[SET < NUM_SETS ? SET : 0], tab.uniW, sizeof(tab.uniW));
+        if (SET < NUM_SETS) {
+            memcpy(h_uniW[SET < NUM_SETS ? SET : 0], tab.uniW, sizeof(tab.uniW));
+            memcpy(h_uniU[SET < NUM_SETS ? SET : 0], tab.uniU, sizeof(tab.uniU));
+        }
     }
     typename T::LanePtrs ptrs(uint32_t lane, int kind) const { return T::lane_ptrs(tab.block[kind].data(), lane); }
 
-    // k_polymul_dq (FP64-quotient butterflies, signed-lazy sets): same phases; the denormal-operand fma runs on the host FPU.
-    // `stats` (optional): [0] largest |true value| / q seen at a transposition or at the end of a pass (offset form removed)
+    // k_polymul_dq (FP64-quotient butterflies, signed-lazy sets): same phases; the denormal arithmetic runs on the host FPU.
+    // `stats` (optional): [0] largest |true value| / q seen at the end of a pass (offset form removed); 1e9 if the high
+    // half of a register pair was ever non-zero
     void polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, double* stats) {
         if constexpr (T::LAZY) {
+            using P64 = typename T::P64;
             alignas(16) static uint32_t bufA[64 * 32], bufB[64 * 32];
             const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
-            std::vector<uint64_t> V(32 * E);
-            auto v = [&](uint32_t lane) -> uint64_t(&)[E] { return *reinterpret_cast<uint64_t(*)[E]>(&V[lane * E]); };
+            std::vector<P64> V(32 * E);
+            auto v = [&](uint32_t lane) -> P64(&)[E] { return *reinterpret_cast<P64(*)[E]>(&V[lane * E]); };
             double worst = 0;
+            const uint64_t one = 1;
+            double tiny;
+            memcpy(&tiny, &one, sizeof tiny);  // the denormal 2^-1074
+            auto seed = [&](uint32_t r) { return P64{tiny * h_uniW[SET < NUM_SETS ? SET : 0][UNI_FWD][r]}; };
             auto track = [&](uint32_t lane) {
                 for (uint32_t r = 0; r < E; r++) {
-                    if (V[lane * E + r] >> 32) worst = 1e9;  // the high half must stay zero
-                    const double t = std::fabs((double)(int64_t)((int64_t)(uint32_t)V[lane * E + r] - (int64_t)T::DQ_OFF)) / (double)T::Q;
+                    if (V[lane * E + r].hi() != 0) worst = 1e9;  // the high half must stay zero
+                    const double t = std::fabs((double)((int64_t)V[lane * E + r].lo() - (int64_t)T::DQ_OFF)) / (double)T::Q;
                     worst = t > worst ? t : worst;
                 }
             };
@@ -53,21 +63,19 @@ template <int SET> struct Emu {
                     uint32_t* st = op ? bufB : bufA;
                     const uint32_t* g = (op ? y : x) + base;
                     for (uint32_t l = 0; l < 32; l++) {
-                        for (uint32_t r = 0; r < E; r++) v(l)[r] = valid(l) ? g[T::row_off(l, r)] : 0u;
+                        for (uint32_t r = 0; r < E; r++) v(l)[r] = seed(r).with_lo(valid(l) ? g[T::row_off(l, r)] : 0u);
                         T::fwd_rows_dq(v(l));
                         track(l);
                     }
                     for (uint32_t l = 0; l < 32; l++)
-                        for (uint32_t r = 0; r < E; r++) st[T::swz(T::row_off(l, r))] = (uint32_t)v(l)[r];
+                        for (uint32_t r = 0; r < E; r++) st[T::swz(T::row_off(l, r))] = v(l)[r].lo();
                     for (uint32_t l = 0; l < 32; l++)
-                        for (uint32_t r = 0; r < E; r++) v(l)[r] = st[T::swz(E * l + r)];
+                        for (uint32_t r = 0; r < E; r++) v(l)[r] = seed(r).with_lo(st[T::swz(E * l + r)]);
                     for (uint32_t l = 0; l < 32; l++) {
-                        const auto P = ptrs(l, 1);
-                        const auto PW = T::lane_ptrs_w(tab.blockW[1].data(), l);
-                        T::fwd_cols_dq(v(l), P.fwd, PW.fwd);
+                        T::fwd_cols_dq(v(l), T::lane_ptrs_dq(tab.blockU[1].data(), tab.blockW[1].data(), l));
                         track(l);
                         if (op == 0)
-                            for (uint32_t r = 0; r < E; r++) bufA[T::swz(E * l + r)] = (uint32_t)v(l)[r];
+                            for (uint32_t r = 0; r < E; r++) bufA[T::swz(E * l + r)] = v(l)[r].lo();
                     }
                 }
                 for (uint32_t l = 0; l < 32; l++) {
@@ -76,13 +84,12 @@ template <int SET> struct Emu {
                     track(l);
                 }
                 for (uint32_t l = 0; l < 32; l++)
-                    for (uint32_t r = 0; r < E; r++) bufB[T::swz(E * l + r)] = (uint32_t)v(l)[r];
+                    for (uint32_t r = 0; r < E; r++) bufB[T::swz(E * l + r)] = v(l)[r].lo();
                 for (uint32_t l = 0; l < 32; l++)
-                    for (uint32_t r = 0; r < E; r++) v(l)[r] = bufB[T::swz(T::row_off(l, r))];
+                    for (uint32_t r = 0; r < E; r++) v(l)[r] = seed(r).with_lo(bufB[T::swz(T::row_off(l, r))]);
                 for (uint32_t l = 0; l < 32; l++) {
                     uint32_t out[E];
-                    T::inv_rows_dq(v(l), out, ptrs(l, 1), T::lane_ptrs_w(tab.blockW[1].data(), l));
-                    track(l);
+                    T::inv_rows_dq(v(l), out, T::lane_ptrs_dq(tab.blockU[1].data(), tab.blockW[1].data(), l));
                     T::store_rows(out, z + base, l, valid(l));
                 }
             }
@@ -448,14 +455,16 @@ int qtemu_polymul_dq(int set, const uint32_t* x, const uint32_t* y, uint32_t* z,
     EMU_DISPATCH(set, polymul_dq(x, y, z, batch, stats));
     return 0;
 }
-// one FP64-quotient product y*w - rint(y w / q) q for every (y, w) pair: out = the signed remainder
-int qtemu_dq_remainder(int set, const uint32_t* y, const int32_t* w, int32_t* out, size_t count) {
+// one FP64-quotient product y*w - rint(y w / q) q for every (y, w) pair, w in [0, q): out = the signed remainder
+int qtemu_dq_remainder(int set, const uint32_t* y, const uint32_t* w, int32_t* out, size_t count) {
     if (set != SET_I && set != SET_III) return -4;
     for (size_t i = 0; i < count; i++) {
         const uint32_t q = set == SET_I ? Cfg<SET_I>::Q : Cfg<SET_III>::Q;
-        const double W = dq_companion((uint32_t)w[i], q);
-        const uint32_t qe = set == SET_I ? Tile<SET_I>::dq_quot((uint64_t)y[i], W) : Tile<SET_III>::dq_quot((uint64_t)y[i], W);
-        out[i] = (int32_t)(y[i] * (uint32_t)w[i] - qe * q);
+        const double W = dq_companion(w[i], q);
+        const auto yy = Tile<SET_III>::P64::make(y[i], 0u);
+        const auto t = Tile<SET_III>::dq_quot(yy, W);
+        if (t.hi() != 0) return -5;  // the quotient must come out as {integer, 0}
+        out[i] = (int32_t)(y[i] * w[i] - t.lo() * q);
     }
     return 0;
 }

@@ -31,7 +31,7 @@ def emu():
     L.qtemu_inner_lazy.argtypes = [C.c_int, u, u, u, C.c_size_t]
     L.qtemu_row_f64.argtypes = [C.c_int, u, u, u, C.c_size_t]
     L.qtemu_polymul_dq.argtypes = [C.c_int, u, u, u, C.c_size_t, C.POINTER(C.c_double)]
-    L.qtemu_dq_remainder.argtypes = [C.c_int, u, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_size_t]
+    L.qtemu_dq_remainder.argtypes = [C.c_int, u, u, C.POINTER(C.c_int32), C.c_size_t]
     return L
 
 
@@ -216,18 +216,19 @@ def test_harvey_range_plan_of_p_I(emu):
 
 @pytest.mark.parametrize("s", [SET_I, SET_III])
 def test_fp64_quotient_remainder(emu, oracle, s):
-    """the FP64-quotient product of the DQ butterflies (Tile::dq_quot: one fma on the DENORMAL double whose bit pattern is
-    {y, 0}): for every 32-bit unsigned y and every centred twiddle w, y w - qe q is congruent to y w and lies within
-    q/2 + 1 of zero — what Tile::ct_dq and the range statement in qt_tile.cuh rest on"""
+    """the FP64-quotient product of the DQ butterflies (Tile::dq_quot: the DENORMAL double whose bit pattern is {y, 0}
+    times w / q is the denormal whose bit pattern is {rint(y w / q), 0}): for every 32-bit unsigned y and every twiddle
+    w in [0, q), y w - qe q is congruent to y w and lies within q/2 + 1 of zero — what Tile::ct_dq and the range
+    statement in qt_tile.cuh rest on"""
     q = oracle.params(s).q
     rng = np.random.default_rng(50 + s)
     n = 1 << 18
     y = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
-    w = rng.integers(-(q // 2), q // 2 + 1, n, dtype=np.int64).astype(np.int32)
+    w = rng.integers(0, q, n, dtype=np.uint64).astype(np.uint32)
     y[:8] = [0, 1, q - 1, q, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF]
-    w[:8] = [q // 2, -(q // 2), q // 2, -(q // 2), q // 2, -(q // 2), 1, -1]
+    w[:8] = [q - 1, q - 1, q // 2, q // 2 + 1, q - 1, q // 2, 1, 0]
     out = np.zeros(n, dtype=np.int32)
-    assert emu.qtemu_dq_remainder(s, _p(y), w.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data_as(C.POINTER(C.c_int32)), n) == 0
+    assert emu.qtemu_dq_remainder(s, _p(y), _p(w), out.ctypes.data_as(C.POINTER(C.c_int32)), n) == 0
     r = out.astype(np.int64)
     assert np.abs(r).max() <= q // 2 + 1
     assert np.array_equal(r % q, (y.astype(object) * w.astype(object) % q).astype(np.int64))
