@@ -683,9 +683,12 @@ def main():
             e2.close()
         st = max(3, min(args.steps, 50))
         variants = {}
-        for vname, v in (("direct_loads", 1), ("tma_staged", 2), ("split_tile_n2048", 3), ("split_tile_two_warps_n2048", 4)):
-            if v >= 3 and p.n != 2048:
+        for vname, v in (("direct_loads", 1), ("tma_staged", 2), ("split_tile_n2048", 3), ("split_tile_two_warps_n2048", 4),
+                         ("tma_staged_fp64_quotient", 5)):
+            if v in (3, 4) and p.n != 2048:
                 continue  # the split tile exists for n = 2048 only
+            if v == 5 and p.q >= (1 << 25):
+                continue  # FP64-quotient butterflies: the 23-bit moduli only (measured alternative)
             try:
                 e2, _, ms2, _ = run_config(set_id, batch, st, 3, variant=v)
                 variants[vname] = batch * st / (ms2 * 1e-3)

@@ -97,7 +97,10 @@ int qt_synchronize(qt_ctx* ctx);
 /* fused-kernel data path: 0 = automatic, 1 = direct coalesced loads, 2 = TMA bulk copies staged
  * through shared memory with an mbarrier (needs 16-byte aligned operands), 3 = n=2048 only: TMA-staged
  * with the polynomial processed as two 1024-point halves by one warp, 4 = n=2048 only: the same two halves by a
- * PAIR of warps side by side (what "automatic" picks for qTESLA-p-III) */
+ * PAIR of warps side by side (what "automatic" picks for qTESLA-p-III), 5 = the 23-bit moduli only (qTESLA-I, -III): TMA-staged
+ * with the butterflies' quotient estimate taken from the FP64 pipe instead of a mul.hi (bit-identical results; measured
+ * slower than 2 on B200 and therefore never picked automatically — DESIGN.md 10); QT_ERR_UNSUPPORTED where a variant does
+ * not exist for the context's parameter set */
 int qt_set_fused_variant(qt_ctx* ctx, int variant);
 /* row products of the Z_q Nussbaumer kernels: 0 = automatic, 1 = schoolbook (the structure of the reference's
  * `naive`, NTT.cu:147-165), 2 = recursive (the 2m length-r products are split once more, 32 = 4*8 / 64 = 8*8),

@@ -212,7 +212,8 @@ class Engine:
         _check(lib().qt_set_stream(self._h, cuda_stream))
 
     def set_fused_variant(self, variant):
-        """0 automatic, 1 direct coalesced loads, 2 TMA bulk copies staged through shared memory"""
+        """0 automatic, 1 direct coalesced loads, 2 TMA bulk copies staged through shared memory, 3 / 4 n=2048 as two halves
+        (one warp / a pair of warps), 5 FP64-quotient butterflies (qTESLA-I, -III)"""
         _check(lib().qt_set_fused_variant(self._h, variant))
 
     def set_launch_overlap(self, mode):
