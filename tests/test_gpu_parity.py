@@ -74,7 +74,7 @@ def test_fuzz_batches_sets_variants(engines, oracle):
         s = int(rng.integers(0, 4))
         eng = engines[s]
         B = int(special[it % len(special)] if it % 3 == 0 else rng.integers(1, 3000))
-        variant = int(rng.choice([0, 1, 2] + ([3, 4] if s == 3 else [])))
+        variant = int(rng.choice([0, 1, 2] + ([3, 4] if s == 3 else []) + ([5] if s in (0, 1) else [])))
         eng.set_fused_variant(variant)
         try:
             x, y = rand_pair(eng.q, B * eng.n, 5000 + it)
@@ -104,6 +104,15 @@ def test_fused_variants_agree_at_full_size(engines, s):
     assert torch.equal(z1, z2)
     eng.polymul(x, y, z2); eng.synchronize()      # automatic choice (n=2048: two warps per polynomial)
     assert torch.equal(z1, z2)
+    if s in (0, 1):                               # FP64-quotient butterflies: full batch, worst-case operands, a ragged batch
+        eng.set_fused_variant(5)
+        z2.zero_(); eng.polymul(x, y, z2); eng.synchronize()
+        assert torch.equal(z1, z2)
+        x.fill_(eng.q - 1); y.fill_(eng.q - 1)
+        eng.set_fused_variant(2); eng.polymul(x, y, z1)
+        eng.set_fused_variant(5); z2.zero_(); eng.polymul(x, y, z2, B - 149); eng.synchronize()
+        assert torch.equal(z1[: (B - 149) * eng.n], z2[: (B - 149) * eng.n]) and not z2[(B - 149) * eng.n:].any()
+        eng.set_fused_variant(0)
     if s == 3:
         for v in (3, 4):                          # both split-tile kernels, full batch and a ragged one
             eng.set_fused_variant(v)
