@@ -975,9 +975,21 @@ template <int SET, int RING, int MODE = 0, bool LIFT = false> struct NussBlk {
         else Nuss<SET, 1>::product_recursive(xr, yr);
     }
 
-    // everything of block H up to its inverse stages; result in v
+#ifndef QT_NUSS_BLK_LOCKSTEP
+#define QT_NUSS_BLK_LOCKSTEP 0
+#endif
+    // LOCKSTEP (64-column rows only): the warps of a CTA enter every phase together (CTA barriers), so that the straight-line code
+    // of a phase — the row products alone are ~100 KiB — is fetched once per CTA and phase instead of once per drifting warp
+    static constexpr bool LOCKSTEP = QT_NUSS_BLK_LOCKSTEP && R == 64;
+    static __device__ __forceinline__ void phase_barrier() {
+        if (LOCKSTEP) __syncthreads();
+    }
+    // everything of block H up to its inverse stages; result in v.  `act`: this warp has a polynomial (LOCKSTEP: warps without one
+    // still walk through the barriers)
     template <uint32_t H> static __device__ __forceinline__ void block(Row (&v)[M], const uint32_t* gx, const uint32_t* gy,
-                                                                     uint32_t* sx, uint32_t* sy, uint32_t lane, bool twist) {
+                                                                     uint32_t* sx, uint32_t* sy, uint32_t lane, bool twist, bool act = true) {
+        phase_barrier();
+        if (act) {
 #pragma unroll 1
         for (int op = 0; op < 2; op++) {
 #pragma unroll
@@ -1019,8 +1031,14 @@ template <int SET, int RING, int MODE = 0, bool LIFT = false> struct NussBlk {
                 for (uint32_t e = 0; e < EPL; e++) s[i * RS + lane + 32 * e] = v[i].c[e];
         }
         __syncwarp();
+        }
+        phase_barrier();
+        if (act) {
         product_row(sx + lane * RS, sy + lane * RS);
         __syncwarp();
+        }
+        phase_barrier();
+        if (act) {
 #pragma unroll
         for (uint32_t i = 0; i < M; i++)
 #pragma unroll
@@ -1030,6 +1048,7 @@ template <int SET, int RING, int MODE = 0, bool LIFT = false> struct NussBlk {
         if (TWIST && twist) {
 #pragma unroll
             for (uint32_t i = 1; i < M; i++) v[i] = rot_inv(v[i], i * UNIT, lane);
+        }
         }
     }
 };
@@ -1052,9 +1071,13 @@ k_nussbaumer_blk(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch
     // 2^32 mod q with its Shoup companion: removes the Montgomery factor of the canonical 32-column row products
     const TwPair rfix{T::C::R_MODQ, (uint32_t)(((uint64_t)T::C::R_MODQ << 32) / T::Q)};
     const size_t stride = (size_t)gridDim.x * NB::WARPS;
-    for (size_t p = (size_t)warp * gridDim.x + blockIdx.x; p < batch; p += stride) {  // SM-interleaved
-        const uint32_t* gx = x + p * K::N;
-        const uint32_t* gy = y + p * K::N;
+    // LOCKSTEP: a CTA-uniform loop (warp 0's polynomial index decides), warps past the end of the batch only keep the barriers company
+    for (size_t p0 = blockIdx.x; p0 < batch; p0 += stride) {
+        const size_t p = p0 + (size_t)warp * gridDim.x;  // SM-interleaved
+        const bool act = p < batch;
+        if (!NB::LOCKSTEP && !act) break;
+        const uint32_t* gx = x + (act ? p : 0) * K::N;
+        const uint32_t* gy = y + (act ? p : 0) * K::N;
         if (p + stride < batch) {  // next polynomial of this warp: its lines towards L2 while this one is computed
 #pragma unroll
             for (uint32_t e = 0; e < EPL; e++) {
@@ -1066,8 +1089,8 @@ k_nussbaumer_blk(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch
         if constexpr (NB::TWIST) {
 #pragma unroll 1
             for (uint32_t h = 0; h < 2; h++) {  // one copy of the stage code for both blocks
-                NB::template block<0>(v, gx, gy, sx, sy, lane, h != 0);
-                if (h == 0) {
+                NB::template block<0>(v, gx, gy, sx, sy, lane, h != 0, act);
+                if (h == 0 && act) {
 #pragma unroll
                     for (uint32_t i = 0; i < M; i++)
 #pragma unroll
@@ -1075,13 +1098,16 @@ k_nussbaumer_blk(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch
                 }
             }
         } else {
-            NB::template block<0>(v, gx, gy, sx, sy, lane, false);
+            NB::template block<0>(v, gx, gy, sx, sy, lane, false, act);
+            if (act) {
 #pragma unroll
-            for (uint32_t i = 0; i < M; i++)
+                for (uint32_t i = 0; i < M; i++)
 #pragma unroll
-                for (uint32_t e = 0; e < EPL; e++) sp[i * RS + lane + 32 * e] = v[i].c[e];
-            NB::template block<1>(v, gx, gy, sx, sy, lane, false);
+                    for (uint32_t e = 0; e < EPL; e++) sp[i * RS + lane + 32 * e] = v[i].c[e];
+            }
+            NB::template block<1>(v, gx, gy, sx, sy, lane, false, act);
         }
+        if (!act) continue;
         // last inverse stage (rows i and m+i, no rotation, NTT.cu:241-269 with j = log2 m) and the recombination
         // z[m a + i] = Z_i[a] + Z_{m+i}[a-1], a = 0 wraps with a sign (NTT.cu:271-276)
 #pragma unroll
