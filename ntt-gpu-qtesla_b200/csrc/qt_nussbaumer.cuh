@@ -701,6 +701,33 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
             // non-zero value is never 0).  So each chain is summed exactly in three 32-bit limbs (one
             // multiply-add-with-carry per term) and folded once with the same end-around-carry adds — bit for
             // bit the reference's result, including which representation of zero comes out.
+#ifndef QT_NUSS_RING_HALVES
+#define QT_NUSS_RING_HALVES 0  // measured (run r02D): 39.0 vs 50.0 M polymul/s at n=1024, 88.9 vs 136.9 at n=512 — bit-exact, but two wide
+#endif                          // multiplies per term cost more multiply-pipe time than one multiply + two carry additions; kept for A/B
+            using O0 = NussOps<SET, 0>;
+            if (QT_NUSS_RING_HALVES) {
+                // A/B variant (off).  The same exact sums without a carry chain: y = ylo + 2^16 yhi, and a chain's T = L + 2^16 H with L = sum x ylo,
+                // H = sum x yhi — at most 32 products below 2^48 each, so L and H fit 64-bit accumulators as they are (one
+                // IMAD.WIDE per half and term instead of multiply + two carry additions).  In Z/(2^32-1) 2^32 = 1 and 2^16 is a
+                // rotation by 16 bits, end-around-carry addition is associative and never turns a non-zero operand into 0, so
+                // fold(L) (+) rotl16(fold(H)) is the same word as the fold of T's own limbs — including which zero comes out.
+                uint32_t ylo[32], yhi[32];
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) { ylo[j] = y[j] & 0xFFFFu; yhi[j] = y[j] >> 16; }
+#pragma unroll
+                for (uint32_t k = 0; k < 32; k++) {
+                    uint64_t al = 0, ah = 0, bl = 0, bh = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++) {
+                        if (j <= k) { al += (uint64_t)x[j] * ylo[(k - j) & 31]; ah += (uint64_t)x[j] * yhi[(k - j) & 31]; }
+                        else { bl += (uint64_t)x[j] * ylo[(32 + k - j) & 31]; bh += (uint64_t)x[j] * yhi[(32 + k - j) & 31]; }
+                    }
+                    const uint32_t fa = O0::fold(ah), fb = O0::fold(bh);
+                    const uint32_t A = O0::add(O0::fold(al), __funnelshift_l(fa, fa, 16));
+                    const uint32_t B = O0::add(O0::fold(bl), __funnelshift_l(fb, fb, 16));
+                    xr[k] = O0::sub(A, B);
+                }
+            } else {
 #pragma unroll
             for (uint32_t k = 0; k < 32; k++) {
                 uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
@@ -713,8 +740,8 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                         asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
                             : "+r"(b0), "+r"(b1), "+r"(b2) : "r"(x[j]), "r"(y[(32 + k - j) & 31]));
                 }
-                using O0 = NussOps<SET, 0>;
                 xr[k] = O0::sub(O0::add(O0::add(a0, a1), a2), O0::add(O0::add(b0, b1), b2));
+            }
             }
         } else if (LAZYQ) {
             // 2^32 (the Montgomery factor) times 2^-(LOGM+1) (every halving of the inverse stages), signed Shoup form
