@@ -597,6 +597,10 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
 #define QT_NUSS_SIGN_MAD 0  // measured (run r02w): 80.9 vs 87.5 M polymul/s at n=1024, 210.8 vs 219.4 at n=512 — rejected, kept for A/B
 #endif
     static constexpr bool SIGN_MAD = QT_NUSS_SIGN_MAD && F64;            // signed rotations as multiply-adds (forward() below)
+    // shift-based reduction before the FP64 row products (k_nussbaumer_warp): (2^LOGM + 2) (q - 2^QS) below q/2, and the inverse
+    // stages (additions only, 2^(LOGM+2) times a row-product output of at most q/2 + 1) inside an int32
+    static constexpr bool F64_SHIFT_OK = !F64 || ((((uint64_t)1 << LOGM) + 2) * (Q - (1u << T::QS)) < Q / 2 &&
+                                                  ((uint64_t)4 << LOGM) * (Q / 2 + 2) < (1ull << 31));
     static constexpr uint32_t RS = 33;                                   // row stride in shared memory
     static constexpr uint32_t WARP_WORDS = 2 * ROWS * RS;                // X rows then Y rows
 #ifndef QT_NUSS_WARPS
@@ -841,11 +845,25 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
             for (uint32_t i = 0; i < K::M; i++) v[i + K::M] = v[i];  // rows m..2m-1 are copies (NTT.cu:187-191)
             W::forward(v, lane);
             if constexpr (W::F64) {
-                // FP64 row products take operands in [-q/2, 3q/2); x also takes 2^-(LOGM+1), the halvings of the inverse stages
-                const TwPair one{1u, T::C::MU32}, halves = tw_signed_c(c_powmod((T::Q + 1) / 2, K::LOGM + 1, T::Q), T::Q);
-                const TwPair sw{op ? one.w : halves.w, op ? one.ws : halves.ws};
+                // FP64 row products take operands in [-q/2, 3q/2).
+#ifndef QT_NUSS_F64_SHIFT_RED
+#define QT_NUSS_F64_SHIFT_RED 1
+#endif
+                if (QT_NUSS_F64_SHIFT_RED) {
+                    // q = 2^QS + d with a small d and |v| <= 2^LOGM q after the forward stages: k = v >> QS is within one of
+                    // v / q, so v - k q = (v mod 2^QS) - k d lies in (-(2^LOGM + 2) d, 2^QS + (2^LOGM + 2) d) — a shift and ONE
+                    // multiply-add per coefficient instead of the three multiplies of a Shoup reduction (W::F64_SHIFT_OK).  The
+                    // halvings of the inverse stages, which the Shoup form carried on x, move to the final multiplication.
+                    static_assert(W::F64_SHIFT_OK, "shift-based reduction: range");
 #pragma unroll
-                for (uint32_t r = 0; r < W::ROWS; r++) v[r] = T::smul_shoup(v[r], sw);
+                    for (uint32_t r = 0; r < W::ROWS; r++) v[r] -= (uint32_t)((int32_t)v[r] >> T::QS) * T::Q;
+                } else {
+                    // x also takes 2^-(LOGM+1), the halvings of the inverse stages
+                    const TwPair one{1u, T::C::MU32}, halves = tw_signed_c(c_powmod((T::Q + 1) / 2, K::LOGM + 1, T::Q), T::Q);
+                    const TwPair sw{op ? one.w : halves.w, op ? one.ws : halves.ws};
+#pragma unroll
+                    for (uint32_t r = 0; r < W::ROWS; r++) v[r] = T::smul_shoup(v[r], sw);
+                }
             }
             uint32_t* s = op ? sy : sx;
 #pragma unroll
@@ -869,7 +887,8 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
                 const uint32_t i = 4 * c + k;
                 const uint32_t up = __shfl_sync(0xffffffffu, v[K::M + i], (lane - 1) & 31u);
                 uint32_t r = (lane == 0) ? O::sub(v[i], up) : O::add(v[i], up);
-                if (W::LAZYQ) r = T::scanon(T::smul_shoup(r, TwPair{1u, T::C::MU32}));  // any |r| < 2^31 -> [0, q)
+                if (W::F64 && QT_NUSS_F64_SHIFT_RED) r = T::scanon(T::smul_shoup(r, tw_signed_c(c_powmod((T::Q + 1) / 2, K::LOGM + 1, T::Q), T::Q)));  // the deferred halvings
+                else if (W::LAZYQ) r = T::scanon(T::smul_shoup(r, TwPair{1u, T::C::MU32}));  // any |r| < 2^31 -> [0, q)
                 else if (RING == 1) r = T::csub(T::mul_shoup(r, rfix), T::Q);
                 else if (LIFT) r = NussOps<SET, 0>::lift_out(r);
                 o[k] = r;
