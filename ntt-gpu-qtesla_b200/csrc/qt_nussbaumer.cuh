@@ -638,7 +638,10 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
     // 16-byte boundaries, so a lane reads and writes its row with 128-bit accesses (a quarter of the shared-memory instructions),
     // which are conflict-free too (lane l covers banks 4l .. 4l+3 mod 32), as is the column access of the stage phases
     // (run r02D: n=1024 96.4 vs 92.9 M polymul/s; n=512, one row per lane: 230.5 vs 232.2 — the 64-row sets only)
-    static constexpr uint32_t RS = (F64 && ROWS == 64) ? QT_NUSS_F64_RS : 33;
+#ifndef QT_NUSS_RS_ALL
+#define QT_NUSS_RS_ALL 1  // every 64-row Z_q warp kernel (schoolbook 77.2 vs 75.3, recursive 79.2 vs 78.1, p-I recursive 57.3 vs 56.6 M
+#endif                    // polymul/s), not only the FP64 rows; the ring 2^32-1 kernels lose (47.3 vs 50.0: spills at 168 registers)
+    static constexpr uint32_t RS = ((F64 || (QT_NUSS_RS_ALL && RING == 1)) && ROWS == 64) ? QT_NUSS_F64_RS : 33;
     static constexpr uint32_t WARP_WORDS = 2 * ROWS * RS;                // X rows then Y rows
 #ifndef QT_NUSS_WARPS
 #define QT_NUSS_WARPS 12
@@ -723,8 +726,28 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
     }
     static __device__ __forceinline__ void product_row_int(uint32_t* xr, const uint32_t* yr) {
         uint32_t x[32], y[32];
+        constexpr bool VEC = RS % 4 == 0;  // rows on 16-byte boundaries: 128-bit loads and stores
+        if (VEC) {
 #pragma unroll
-        for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
+            for (uint32_t c = 0; c < 8; c++) {
+                const U4 u = reinterpret_cast<const U4*>(xr)[c], w = reinterpret_cast<const U4*>(yr)[c];
+                x[4 * c] = u.x; x[4 * c + 1] = u.y; x[4 * c + 2] = u.z; x[4 * c + 3] = u.w;
+                y[4 * c] = w.x; y[4 * c + 1] = w.y; y[4 * c + 2] = w.z; y[4 * c + 3] = w.w;
+            }
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) { x[j] = xr[j]; y[j] = yr[j]; }
+        }
+        uint32_t o4[4];  // outputs leave four at a time
+#define QT_NUSS_PUT(k, val)                                                                             \
+    do {                                                                                                \
+        if (VEC) {                                                                                      \
+            o4[(k) & 3] = (val);                                                                        \
+            if (((k) & 3) == 3) reinterpret_cast<U4*>(xr)[(k) >> 2] = U4{o4[0], o4[1], o4[2], o4[3]};   \
+        } else {                                                                                        \
+            xr[k] = (val);                                                                              \
+        }                                                                                               \
+    } while (0)
         if (REC) {
             // same output convention as the schoolbook branches below: LAZYQ — product * 2^-(LOGM+1) in
             // [-q/2, 3q/2); canonical — product * 2^-32 in [0, q)
@@ -734,7 +757,7 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
             uint32_t zz[32];
             Inner::product(x, y, zz, fix);
 #pragma unroll
-            for (uint32_t j = 0; j < 32; j++) xr[j] = zz[j];
+            for (uint32_t j = 0; j < 32; j++) QT_NUSS_PUT(j, zz[j]);
         } else if (RING == 0) {
             // naive (NTT.cu:147-165) keeps two chains per output, A over j <= k and B over j > k, folding
             // after every term.  A chain's final value is a function of the INTEGER sum T of its products
@@ -766,7 +789,7 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                     const uint32_t fa = O0::fold(ah), fb = O0::fold(bh);
                     const uint32_t A = O0::add(O0::fold(al), __funnelshift_l(fa, fa, 16));
                     const uint32_t B = O0::add(O0::fold(bl), __funnelshift_l(fb, fb, 16));
-                    xr[k] = O0::sub(A, B);
+                    QT_NUSS_PUT(k, O0::sub(A, B));
                 }
             } else {
 #pragma unroll
@@ -781,7 +804,7 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                         asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
                             : "+r"(b0), "+r"(b1), "+r"(b2) : "r"(x[j]), "r"(y[(32 + k - j) & 31]));
                 }
-                xr[k] = O0::sub(O0::add(O0::add(a0, a1), a2), O0::add(O0::add(b0, b1), b2));
+                QT_NUSS_PUT(k, O0::sub(O0::add(O0::add(a0, a1), a2), O0::add(O0::add(b0, b1), b2)));
             }
             }
         } else if (LAZYQ) {
@@ -798,7 +821,7 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                 }
                 const uint32_t m = (uint32_t)acc * (0u - T::C::QINV_NEG);                 // lo(acc) * q^-1
                 const uint32_t red = (uint32_t)(acc >> 32) - (uint32_t)mulhi32s(m, Q);   // acc * 2^-32, |red| < 2^30
-                xr[k] = T::smul_shoup(red, fix);                                          // [-q/2, 3q/2)
+                QT_NUSS_PUT(k, T::smul_shoup(red, fix));                                  // [-q/2, 3q/2)
             }
         } else {
             uint32_t ny[32];
@@ -822,9 +845,10 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                 // canonical: r < (32/TERMS)*2q
                 if (32 / TERMS == 1) r = T::csub(r, Q);
                 else r = T::csub(T::fold2q(r), Q);
-                xr[k] = r;
+                QT_NUSS_PUT(k, r);
             }
         }
+#undef QT_NUSS_PUT
     }
 };
 
