@@ -720,13 +720,13 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
                   "inner product accumulator");
 
     // one row: z = x (*) y negacyclic, length 32; x, y, z are shared-memory rows (z overwrites x)
-    static __device__ __forceinline__ void product_row(uint32_t* xr, const uint32_t* yr) {
-        if constexpr (F64) NussRowF64<SET>::template product<(RS % 4 == 0)>(xr, yr);
-        else product_row_int(xr, yr);
+    // VEC: the rows start on 16-byte boundaries (this kernel's own row stride; the block-pass kernel has its own and passes false)
+    template <bool VEC = (RS % 4 == 0)> static __device__ __forceinline__ void product_row(uint32_t* xr, const uint32_t* yr) {
+        if constexpr (F64) NussRowF64<SET>::template product<VEC>(xr, yr);
+        else product_row_int<VEC>(xr, yr);
     }
-    static __device__ __forceinline__ void product_row_int(uint32_t* xr, const uint32_t* yr) {
+    template <bool VEC> static __device__ __forceinline__ void product_row_int(uint32_t* xr, const uint32_t* yr) {
         uint32_t x[32], y[32];
-        constexpr bool VEC = RS % 4 == 0;  // rows on 16-byte boundaries: 128-bit loads and stores
         if (VEC) {
 #pragma unroll
             for (uint32_t c = 0; c < 8; c++) {
@@ -1077,7 +1077,7 @@ template <int SET, int RING, int MODE = 0, bool LIFT = false> struct NussBlk {
 
     // one row product, rows where they lie in shared memory (z overwrites x)
     static __device__ __forceinline__ void product_row(uint32_t* xr, uint32_t* yr) {
-        if constexpr (R == 32) W::product_row(xr, yr);
+        if constexpr (R == 32) W::template product_row<false>(xr, yr);  // (row stride R + 1 here)
         else if constexpr (RING == 0) Nuss<SET, 0>::product(xr, yr);
         else Nuss<SET, 1>::product_recursive(xr, yr);
     }
@@ -1300,11 +1300,12 @@ template <int SET> int nuss_setup(int num_sms, int* grid) {
         if (o1 < 1) return -4;
     }
     if constexpr (K::R == 32) {  // warp-resident kernels
-        using W = NussWarp<SET, 0>;
+        using W = NussWarp<SET, 0>;      // (each kernel with its OWN geometry: the row stride, and with it the shared-memory
+        using WS = NussWarp<SET, 1, 0>;  //  size, differs between the ring and the Z_q kernels)
         using WR = NussWarp<SET, 1, 1>;
         if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 0, 0>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
         if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 0, 0, true>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
-        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 0>, W::WARPS * 32, W::SMEM_BYTES, &occ))) return rc;
+        if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 0>, WS::WARPS * 32, WS::SMEM_BYTES, &occ))) return rc;
         if ((rc = nuss_prepare(k_nussbaumer_warp<SET, 1, 1>, WR::WARPS * 32, WR::SMEM_BYTES, &occ))) return rc;
         if constexpr (nuss_has_f64<SET>()) {
             using WF = NussWarp<SET, 1, 2>;
@@ -1362,7 +1363,7 @@ int nuss_launch(int max_grid, const uint32_t* x, const uint32_t* y, uint32_t* z,
             if constexpr (nuss_has_f64<SET>())
                 k_nussbaumer_warp<SET, 1, 2><<<g, NussWarp<SET, 1, 2>::WARPS * 32, NussWarp<SET, 1, 2>::SMEM_BYTES, s>>>(x, y, z, batch);
         } else if (rec) k_nussbaumer_warp<SET, 1, 1><<<g, NussWarp<SET, 1, 1>::WARPS * 32, NussWarp<SET, 1, 1>::SMEM_BYTES, s>>>(x, y, z, batch);
-        else k_nussbaumer_warp<SET, 1, 0><<<g, W::WARPS * 32, W::SMEM_BYTES, s>>>(x, y, z, batch);
+        else k_nussbaumer_warp<SET, 1, 0><<<g, NussWarp<SET, 1, 0>::WARPS * 32, NussWarp<SET, 1, 0>::SMEM_BYTES, s>>>(x, y, z, batch);
         return (int)cudaGetLastError();
     } else {
         const size_t groups = (batch + K::P - 1) / K::P;
