@@ -11,6 +11,19 @@
 namespace qt {
 
 constexpr int WARPS_PER_CTA = 8;   // direct-load kernels
+// The warp index as a value the compiler KNOWS to be the same in all lanes (the shuffle of lane 0's copy): tile indices,
+// buffer and barrier addresses and the bulk-copy descriptors derived from it live in uniform registers, the tile loop is
+// uniform control flow, and ptxas stops duplicating the first forward pass around the barrier wait (k_polymul_tma<III>:
+// 2 304 instead of 2 840 static instructions).  Measured per kernel (run r02F): fused n=512 512.1 vs 504.6, p-I 220.0 vs 214.6,
+// n=2048 (pair) 92.4 vs 89.8, n=1024 245.8 vs 245.1 M polymul/s, single forward transform 641.8 vs 629.4 M polynomials/s,
+// Nussbaumer ring 52.5 vs 49.7 — but the natural-order transforms LOSE 12 % (541.9 vs 614.5) and the split-tile cached product
+// 7 % (109.7 vs 117.9), so those kernels (and the direct-load ones, which were not measured) keep the plain index.
+#ifndef QT_UNIFORM_WARP
+#define QT_UNIFORM_WARP 1
+#endif
+template <bool UNIFORM> __device__ __forceinline__ uint32_t warp_index() {
+    return (UNIFORM && QT_UNIFORM_WARP) ? __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) : threadIdx.x >> 5;
+}
 // Geometry of the TMA-staged fused kernel, chosen by measurement on B200 (tools/ab.py):
 // ONE 16-warp CTA per SM beat 2x8, 3x8, 2x12 and 5x4 warps (221 vs 208-215 M polymul/s at n=1024).
 #ifndef QT_TMA_WARPS
@@ -96,7 +109,7 @@ k_polymul(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, const
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
 
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<false>(), lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
     const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
@@ -204,7 +217,7 @@ k_polymul_tma(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, c
     const int NW = (int)(blockDim.x >> 5);  // <= TmaCfg<SET>::WARPS; small batches are launched with fewer warps (less shared memory: the next launch's CTA fits beside this one)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * G::BUFS * G::WORDS);
 
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<true>(), lane = threadIdx.x & 31;
     uint32_t* A = s_stage + warp * G::BUFS * G::WORDS;
     uint32_t* B = A + G::WORDS;
     uint64_t* bar_a = s_bar + 2 * warp;
@@ -335,7 +348,7 @@ k_polymul_dq(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, co
     const int NW = (int)(blockDim.x >> 5);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
 
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<true>(), lane = threadIdx.x & 31;
     uint32_t* A = s_stage + warp * 2 * G::WORDS;
     uint32_t* B = A + G::WORDS;
     uint64_t* bar_a = s_bar + 2 * warp;
@@ -491,7 +504,7 @@ k_polymul_split(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch,
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
     const int NW = (int)(blockDim.x >> 5);  // <= SplitShape::WARPS
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<false>(), lane = threadIdx.x & 31;
     uint32_t* A = s_stage + warp * 2 * G::WORDS;
     uint32_t* B = A + G::WORDS;
     uint64_t* bar_a = s_bar + 2 * warp;
@@ -642,7 +655,7 @@ k_polymul_pair(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batch, 
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
     const int NP = (int)(blockDim.x >> 6);  // pairs in this CTA (<= PairShape::PAIRS)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NP * 2 * G::WORDS);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp >> 1, h = warp & 1;
+    const uint32_t warp = warp_index<true>(), lane = threadIdx.x & 31, pair = warp >> 1, h = warp & 1;
     uint32_t* A = s_stage + pair * 2 * G::WORDS;
     uint32_t* B = A + G::WORDS;
     uint64_t* bar_a = s_bar + 2 * pair;
@@ -749,7 +762,7 @@ k_ntt_split(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + T::TABLE_QUADS);
     const int NW = (int)(blockDim.x >> 5);  // <= SplitShape::WARPS
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<false>(), lane = threadIdx.x & 31;
     uint32_t* buf0 = s_stage + warp * 2 * G::WORDS;
     uint64_t* bar0 = s_bar + 2 * warp;
     const size_t stride = (size_t)gridDim.x * NW;
@@ -850,7 +863,7 @@ k_polymul_ntt(const uint32_t* __restrict__ a_hat, const uint32_t* y, uint32_t* z
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
     const int NW = (int)(blockDim.x >> 5);  // <= TmaCfg<SET>::WARPS; small batches are launched with fewer warps (less shared memory: the next launch's CTA fits beside this one)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<true>(), lane = threadIdx.x & 31;
     // One y buffer per warp, refilled as soon as the inverse has left it (measured: requesting the next y a
     // whole tile ahead into a second buffer is not faster for these sets, and slower for n=512)
     uint32_t* B = s_stage + warp * 2 * G::WORDS;
@@ -936,7 +949,7 @@ k_ntt_forward(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<false>(), lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
     const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
@@ -972,7 +985,7 @@ k_ntt_inverse(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<false>(), lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
     const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
@@ -1010,7 +1023,7 @@ k_ntt_natural(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     uint32_t* s_buf = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
     copy_table_to_smem(s_tw, g_lane, S::TW_QUADS);
     __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<false>(), lane = threadIdx.x & 31;
     uint32_t* buf = s_buf + warp * T::C::TILE_WORDS;
     const typename T::LanePtrs P = T::lane_ptrs(s_tw, lane);
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
@@ -1056,7 +1069,7 @@ k_ntt_tma(uint32_t* a, size_t batch, const TwQuad* __restrict__ g_lane) {
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tw + S::TW_QUADS);
     const int NW = (int)(blockDim.x >> 5);  // <= TmaCfg<SET>::WARPS; small batches are launched with fewer warps (less shared memory: the next launch's CTA fits beside this one)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + NW * 2 * G::WORDS);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = warp_index<true>(), lane = threadIdx.x & 31;
     uint32_t* buf0 = s_stage + warp * 2 * G::WORDS;
     uint64_t* bar0 = s_bar + 2 * warp;
     const size_t ntiles = (batch + T::PPW - 1) / T::PPW;
@@ -1174,7 +1187,7 @@ k_bitrev_copy(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_
     using S = BitrevShape<SET>;
     constexpr uint32_t R = S::R, LOGR = S::LOGR;
     extern __shared__ uint4 smem_raw[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = warp_index<false>();
     uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw) + warp * S::WARP_WORDS;
     const uint32_t rl = __brev(lane) >> 27;  // brv5(lane): the output run this lane's inputs belong to
     const size_t warps = (size_t)gridDim.x * S::WARPS;
