@@ -71,12 +71,15 @@ __device__ __forceinline__ void pdl_wait() {
 #ifndef QT_FUSED_WARPS_P_I
 #define QT_FUSED_WARPS_P_I 24
 #endif
+#ifndef QT_FUSED_WARPS_I
+#define QT_FUSED_WARPS_I QT_TMA_WARPS
+#endif
 template <int SET> struct TmaCfg {
     // single transforms and the cached-transform product (run r02w, 16 / 20 / 24 warps): n=1024 forward 617 / 625 / 479 M
     // polynomials/s (p-I 585 / 602 / 501), cached product 359 / 360 / 356; n=512 forward 1206 / 1182 / 1175, cached 737 / 708 / 702
     static constexpr int WARPS = (Cfg<SET>::E == 64) ? QT_TMA_WARPS_E64 : (Cfg<SET>::N == 512 ? QT_TMA_WARPS : QT_TMA_WARPS_N1024);
     static constexpr int FUSED_WARPS = (Cfg<SET>::E == 64) ? QT_TMA_WARPS_E64
-                                       : SET == SET_III ? QT_FUSED_WARPS_III : SET == SET_P_I ? QT_FUSED_WARPS_P_I : QT_TMA_WARPS;
+                                       : SET == SET_III ? QT_FUSED_WARPS_III : SET == SET_P_I ? QT_FUSED_WARPS_P_I : QT_FUSED_WARPS_I;
     static constexpr int MAX_WARPS = WARPS > FUSED_WARPS ? WARPS : FUSED_WARPS;
     static constexpr int MINB = (Cfg<SET>::E == 64) ? 1 : QT_TMA_MINB;  // 64 coefficients per thread need the registers
 };
