@@ -690,6 +690,29 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
         }
     }
 
+    // both operands through the stages TOGETHER: one copy of the lane predicates and shuffle indices, twice the independent work
+    // between a shuffle and its use (A/B: QT_NUSS_F64_PAIRED)
+    static __device__ __forceinline__ void forward2(uint32_t (&v)[ROWS], uint32_t (&u)[ROWS], uint32_t lane) {
+#pragma unroll
+        for (int j = (int)LOGM - 1; j >= 0; j--) {
+#pragma unroll
+            for (uint32_t bf = 0; bf < M; bf++) {
+                const uint32_t i = bf >> j, t = bf & ((1u << j) - 1);
+                const uint32_t I = (i << (j + 1)) + t, L = I + (1u << j), sr = rot(i, (uint32_t)j);
+                uint32_t tv = v[L], tu = u[L];
+                const uint32_t vi = v[I], ui = u[I];
+                if (sr != 0) {
+                    const uint32_t sv = __shfl_sync(0xffffffffu, tv, (lane - sr) & 31u), su = __shfl_sync(0xffffffffu, tu, (lane - sr) & 31u);
+                    const bool keep = lane >= sr;
+                    tv = keep ? sv : O::neg(sv);
+                    tu = keep ? su : O::neg(su);
+                }
+                v[L] = O::sub(vi, tv); v[I] = O::add(vi, tv);
+                u[L] = O::sub(ui, tu); u[I] = O::add(ui, tu);
+            }
+        }
+    }
+
     static __device__ __forceinline__ void inverse(uint32_t (&z)[ROWS], uint32_t lane) {
 #pragma unroll
         for (uint32_t j = 0; j <= LOGM; j++) {
@@ -855,6 +878,9 @@ template <int SET, int RING, int MODE = 0> struct NussWarp {
 #ifndef QT_NUSS_PREFETCH
 #define QT_NUSS_PREFETCH 1
 #endif
+#ifndef QT_NUSS_F64_SHIFT_RED
+#define QT_NUSS_F64_SHIFT_RED 1
+#endif
 #ifndef QT_NUSS_UNIFORM_WARP
 #define QT_NUSS_UNIFORM_WARP 1  // the warp index as a provably warp-uniform value (see qt_kernels.cuh: warp_index); run r02F: ring
                                 // 2^32-1 52.5 vs 49.7, n=512 FP64 rows 236.1 vs 232.7, n=1024 FP64 rows 96.4 vs 96.3 M polymul/s
@@ -889,6 +915,31 @@ k_nussbaumer_warp(const uint32_t* x, const uint32_t* y, uint32_t* z, size_t batc
         }
 #endif
         uint32_t v[W::ROWS];
+#ifndef QT_NUSS_F64_PAIRED
+#define QT_NUSS_F64_PAIRED 0  // measured (run r02G): 90.8 vs 96.6 M polymul/s at n=1024, 227.6 vs 236.7 at n=512 — rejected, kept for A/B
+#endif
+        constexpr bool PAIRED = QT_NUSS_F64_PAIRED && W::F64 && QT_NUSS_F64_SHIFT_RED && !LIFT;
+        if constexpr (PAIRED) {
+            uint32_t u[W::ROWS];
+            const uint4* gxv = reinterpret_cast<const uint4*>(gx + K::M * lane);
+            const uint4* gyv = reinterpret_cast<const uint4*>(gy + K::M * lane);
+#pragma unroll
+            for (uint32_t c = 0; c < K::M / 4; c++) {
+                const uint4 a = gxv[c], b = gyv[c];
+                v[4 * c] = a.x; v[4 * c + 1] = a.y; v[4 * c + 2] = a.z; v[4 * c + 3] = a.w;
+                u[4 * c] = b.x; u[4 * c + 1] = b.y; u[4 * c + 2] = b.z; u[4 * c + 3] = b.w;
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < K::M; i++) { v[i + K::M] = v[i]; u[i + K::M] = u[i]; }
+            W::forward2(v, u, lane);
+#pragma unroll
+            for (uint32_t r = 0; r < W::ROWS; r++) {
+                v[r] -= (uint32_t)((int32_t)v[r] >> T::QS) * T::Q;
+                u[r] -= (uint32_t)((int32_t)u[r] >> T::QS) * T::Q;
+            }
+#pragma unroll
+            for (uint32_t r = 0; r < W::ROWS; r++) { sx[r * W::RS + lane] = v[r]; sy[r * W::RS + lane] = u[r]; }
+        } else
 #pragma unroll 1
         for (int op = 0; op < 2; op++) {
             const uint4* g = reinterpret_cast<const uint4*>((op ? gy : gx) + K::M * lane);  // X_i[a] = x[m*a + i]
