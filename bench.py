@@ -72,7 +72,7 @@ FUSED_KERNEL = {0: "k_polymul_tma<0>", 1: "k_polymul_tma<1>", 2: "k_polymul_tma<
 def newest_ncu(kernel_substr):
     """Newest committed ncu summary (profiles/ncu_*.json, written by tools/ncu_summary.py) of a kernel: returns
     {"capture", "fmaheavy_pct", "alu_pct", "fp64_pct", "issue_pct", "dram_bytes_per_launch", "duration_us"} or None.
-    Runs are ordered by their tag (…_r01t.json < …_r02a.json)."""
+    Runs are ordered by their tag (…_r01t.json < …_r02a.json < …_r02z.json < …_r02A.json)."""
     import glob
     import re
     best = None
@@ -84,8 +84,8 @@ def newest_ncu(kernel_substr):
             continue
         if kernel_substr not in (d.get("kernel") or ""):
             continue
-        m = re.search(r"_r(\d+)([a-z]+)\.json$", path)
-        key = (int(m.group(1)), len(m.group(2)), m.group(2)) if m else (0, 0, "")
+        m = re.search(r"_r(\d+)([A-Za-z]+)\.json$", path)  # run tags: r02a .. r02z, then r02A .. r02Z
+        key = (int(m.group(1)), m.group(2)[0].isupper(), len(m.group(2)), m.group(2)) if m else (0, False, 0, "")
         if best is None or key > best[0]:
             best = (key, path, d)
     if best is None:

@@ -276,8 +276,10 @@ template <int SET, bool SHIFT_OK = true> struct Tile {
     // only for a fraction of the butterflies: every QT_SHIFT_MOD-th one (0 = never).  Measured at n=1024,
     // batch 65 536: never 238.9, every 2nd < 238, 3rd 238.9, 4th 240.9, 5th 240.2, 8th 240.5 M polymul/s.
     // (Inline PTX: written in C the compiler folds the shifts back into one IMAD.)
+    // Re-measured on the final kernel (uniform warp index, run r02I/r02J): never 244.5, every 2nd 240.3, 3rd 248.2, 4th 246.4,
+    // 5th 248.0, 6th 247.6 M polymul/s; the single transforms prefer 4 or 5 (3rd: -3 %), the cached product 5 -> 5.
 #ifndef QT_SHIFT_MOD
-#define QT_SHIFT_MOD 4
+#define QT_SHIFT_MOD 5
 #endif
     static constexpr bool SHIFT_Q = SHIFT_OK && (Q == (1u << 23) + (1u << 14) + 1u) && (QT_SHIFT_MOD != 0);
     static QT_HD void ct(uint32_t& x, uint32_t& y, TwPair t, uint32_t idx = 1) {
